@@ -1,0 +1,98 @@
+// Internal declarations shared by the translation units of libpinnfem.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "pinnfem.h"
+
+// ---------------------------------------------------------------------------
+// error reporting
+// ---------------------------------------------------------------------------
+void pf_set_error(const char* fmt, ...);
+
+#define PF_CUDA_CHECK(expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            pf_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? PF_ERR_NO_DEVICE \
+                                                                                  : PF_ERR_CUDA; \
+        }                                                                                        \
+    } while (0)
+
+#define PF_REQUIRE(cond, ...)         \
+    do {                              \
+        if (!(cond)) {                \
+            pf_set_error(__VA_ARGS__); \
+            return PF_ERR_ARG;        \
+        }                             \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+
+// One node->element incidence as the device sees it (16 bytes of indices plus
+// 32 bytes of geometry, read warp-uniformly by the gather kernels).
+struct PfIncidence {
+    int32_t elem;  // element id
+    int32_t nbr;   // the element's other node
+    int32_t slot;  // BSR slot of block (node, nbr)
+    int32_t flags; // bit0: first incidence of this row that targets `slot`
+};
+
+struct pf_plan {
+    int dim = 2;
+    int64_t nnode = 0, nelem = 0, ndof = 0, nfree = 0, nfixed = 0, nnzb = 0, ninc = 0;
+    int max_degree = 0;
+    bool has_dup = false;
+
+    // host arrays (int64 where they are exposed for bit-exact checks)
+    std::vector<int32_t> conn;        // [nelem][2]
+    std::vector<double> nodes;        // [nnode][dim]
+    std::vector<int64_t> elem_dofs;   // [nelem][2*dim]
+    std::vector<int64_t> free_dofs, fixed_dofs;
+    std::vector<int64_t> bsr_rowptr, bsr_colind, elem_slots;
+    std::vector<int64_t> inc_ptr, inc_elem, inc_nbr, inc_slot, diag_slot;
+    std::vector<uint8_t> inc_first;
+    std::vector<uint8_t> dof_free;    // [ndof] 1 = free
+    std::vector<double> l0, cosv, sinv, centroid;  // per element ([nelem][dim] for centroid)
+
+    // device copies
+    int device = -1;
+    int sm_count = 148;
+    int32_t* d_inc_ptr = nullptr;       // [nnode+1]
+    PfIncidence* d_inc = nullptr;       // [ninc]
+    double4* d_inc_geo = nullptr;       // [ninc] {cos, sin, 1/l0, l0}
+    double4* d_inc_xy = nullptr;        // [ninc] {x_nbr, y_nbr, x_self, y_self}
+    int32_t* d_diag_slot = nullptr;     // [nnode]
+    int2* d_conn = nullptr;             // [nelem]
+    double4* d_elem_geo = nullptr;      // [nelem] {cos, sin, 1/l0, l0}
+    double4* d_elem_xy = nullptr;       // [nelem] {x_i, y_i, x_j, y_j}
+    double* d_centroid = nullptr;       // [nelem][dim]
+    uint8_t* d_dof_free = nullptr;      // [ndof]
+    int32_t* d_free_dofs = nullptr;     // [nfree]
+    int32_t* d_free_index = nullptr;    // [ndof] position in free_dofs or -1
+    int32_t* d_bsr_rowptr = nullptr;    // [nnode+1]
+    int32_t* d_bsr_colind = nullptr;    // [nnzb]
+
+    // growable scratch for deterministic two-stage reductions
+    double* d_work = nullptr;
+    size_t work_bytes = 0;
+
+    // streams / staging for pf_residual_host
+    cudaStream_t host_streams[3] = {nullptr, nullptr, nullptr};
+    double* d_stage[3][4] = {{nullptr}};
+    size_t stage_elems[4] = {0, 0, 0, 0};
+};
+
+int pf_plan_reserve_work(pf_plan* plan, size_t bytes);
+int pf_plan_activate(const pf_plan* plan);  // cudaSetDevice + uploaded check
+
+static inline cudaStream_t pf_stream_of(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -1,0 +1,387 @@
+// Material networks (fp64): SimpleNN (examples/json/generic.py:118-142) wrapped by
+// NNProperty.value (fem/properties.py:150-156): softplus(net(x)) * scale.
+//
+// One CTA handles a tile of points; the (tiny) weight set lives transposed and
+// padded in shared memory, activations live in shared memory with the point
+// index innermost (conflict-free), each thread owns one point in the forward
+// and delta passes and a strided set of (out,in) weight pairs in the gradient
+// pass.  All reductions run in a fixed order (ascending point inside a CTA,
+// ascending CTA across the grid) so results are bitwise reproducible.
+#include "pf_internal.h"
+#include "pf_mlp.cuh"
+
+namespace {
+
+constexpr int PTS = 128;        // points per CTA
+constexpr int PS = PTS + 1;     // padded row stride of the activation tiles
+
+// shared-memory plan of one CTA (in doubles)
+struct SmemPlan {
+    int w_off[PF_MLP_MAX_LAYERS];  // transposed padded weights Wt[in][wp] of hidden layer l
+    int b_off[PF_MLP_MAX_LAYERS];
+    int wo_off, bo_off;            // output layer
+    int act_off;                   // activations: rows = in_dim + L*wp (backward) or 2*max rows (forward)
+    int delta_off;                 // 2 * wp rows (backward only)
+    int dz_off;                    // PTS
+    int total;
+};
+
+__host__ __device__ inline SmemPlan smem_plan(const PfMlpDesc& d, bool backward) {
+    SmemPlan s;
+    int off = 0;
+    for (int l = 0; l < d.L; ++l) {
+        const int in = l == 0 ? d.in_dim : d.w;
+        s.w_off[l] = off;
+        off += in * d.wp;
+        s.b_off[l] = off;
+        off += d.wp;
+    }
+    s.wo_off = off;
+    off += d.wp;
+    s.bo_off = off;
+    off += 2;  // keep 16-byte alignment of what follows
+    s.act_off = off;
+    const int maxrow = d.wp > d.in_dim ? d.wp : d.in_dim;
+    off += (backward ? (d.in_dim + d.L * d.wp) : 2 * maxrow) * PS;
+    s.delta_off = off;
+    if (backward) off += 2 * d.wp * PS;
+    s.dz_off = off;
+    off += PTS;
+    s.total = off;
+    return s;
+}
+
+// Stage theta into shared memory: hidden weights transposed to [in][wp] with zero padding.
+__device__ void stage_weights(const PfMlpDesc& d, const SmemPlan& s, const double* __restrict__ theta,
+                              double* __restrict__ sm) {
+    for (int l = 0; l < d.L; ++l) {
+        const int in = l == 0 ? d.in_dim : d.w;
+        const double* W = theta + d.w_off[l];
+        const double* b = theta + d.b_off[l];
+        for (int q = threadIdx.x; q < in * d.wp; q += blockDim.x) {
+            const int i = q / d.wp, o = q % d.wp;
+            sm[s.w_off[l] + q] = o < d.w ? W[o * in + i] : 0.0;
+        }
+        for (int o = threadIdx.x; o < d.wp; o += blockDim.x) sm[s.b_off[l] + o] = o < d.w ? b[o] : 0.0;
+    }
+    for (int o = threadIdx.x; o < d.wp; o += blockDim.x) sm[s.wo_off + o] = o < d.w ? theta[d.w_off[d.L] + o] : 0.0;
+    if (threadIdx.x == 0) sm[s.bo_off] = theta[d.b_off[d.L]];
+}
+
+// One hidden layer for the calling thread's point: out[o][t] = tanh(b[o] + sum_i Wt[i][o] in[i][t]).
+__device__ __forceinline__ void hidden_layer(const double* __restrict__ Wt, const double* __restrict__ b, int in,
+                                             int wp, const double* __restrict__ a_in, double* __restrict__ a_out,
+                                             int t) {
+    for (int o0 = 0; o0 < wp; o0 += 4) {
+        double acc0 = b[o0], acc1 = b[o0 + 1], acc2 = b[o0 + 2], acc3 = b[o0 + 3];
+        for (int i = 0; i < in; ++i) {
+            const double a = a_in[i * PS + t];
+            const double2 w01 = *reinterpret_cast<const double2*>(Wt + i * wp + o0);
+            const double2 w23 = *reinterpret_cast<const double2*>(Wt + i * wp + o0 + 2);
+            acc0 = fma(w01.x, a, acc0);
+            acc1 = fma(w01.y, a, acc1);
+            acc2 = fma(w23.x, a, acc2);
+            acc3 = fma(w23.y, a, acc3);
+        }
+        a_out[(o0)*PS + t] = tanh(acc0);
+        a_out[(o0 + 1) * PS + t] = tanh(acc1);
+        a_out[(o0 + 2) * PS + t] = tanh(acc2);
+        a_out[(o0 + 3) * PS + t] = tanh(acc3);
+    }
+}
+
+__device__ __forceinline__ void load_input(const PfMlpDesc& d, const double* __restrict__ X,
+                                           const double* __restrict__ centroid, double load_factor, int64_t p,
+                                           int64_t n, double* __restrict__ a0, int t) {
+    if (X) {
+        for (int i = 0; i < d.in_dim; ++i) a0[i * PS + t] = p < n ? X[p * d.in_dim + i] : 0.0;
+    } else {  // [load_factor, x_c(, y_c)]: sorted dict keys of fem/properties.py:116-125
+        a0[t] = load_factor;
+        for (int i = 1; i < d.in_dim; ++i) a0[i * PS + t] = p < n ? centroid[p * (d.in_dim - 1) + (i - 1)] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(PTS) mlp_forward_kernel(PfMlpDesc d, const double* __restrict__ theta, int64_t n,
+                                                          const double* __restrict__ X,
+                                                          const double* __restrict__ centroid, double load_factor,
+                                                          double scale, int positive, double* __restrict__ out) {
+    extern __shared__ __align__(16) double sm[];
+    const SmemPlan s = smem_plan(d, false);
+    stage_weights(d, s, theta, sm);
+    const int t = threadIdx.x;
+    const int64_t p = (int64_t)blockIdx.x * PTS + t;
+    const int maxrow = d.wp > d.in_dim ? d.wp : d.in_dim;
+    double* buf0 = sm + s.act_off;
+    double* buf1 = buf0 + maxrow * PS;
+    load_input(d, X, centroid, load_factor, p, n, buf0, t);
+    __syncthreads();
+    for (int l = 0; l < d.L; ++l) {
+        hidden_layer(sm + s.w_off[l], sm + s.b_off[l], l == 0 ? d.in_dim : d.w, d.wp, buf0, buf1, t);
+        double* tmp = buf0;
+        buf0 = buf1;
+        buf1 = tmp;
+    }
+    double z = sm[s.bo_off];
+    for (int i = 0; i < d.w; ++i) z = fma(sm[s.wo_off + i], buf0[i * PS + t], z);
+    if (p < n) out[p] = pf_mlp_output(z, scale, positive);
+}
+
+// mode 0: reduce parameter gradients over the CTA's points -> gpart[blockIdx.x][n_params]
+// mode 1: per-point Jacobian rows                            -> jac[p][n_params]
+template <int MODE>
+__global__ void __launch_bounds__(PTS) mlp_backward_kernel(PfMlpDesc d, const double* __restrict__ theta, int64_t n,
+                                                           const double* __restrict__ X,
+                                                           const double* __restrict__ centroid, double load_factor,
+                                                           double scale, int positive,
+                                                           const double* __restrict__ g_out,
+                                                           double* __restrict__ dst) {
+    extern __shared__ __align__(16) double sm[];
+    const SmemPlan s = smem_plan(d, true);
+    stage_weights(d, s, theta, sm);
+    const int t = threadIdx.x;
+    const int64_t p0 = (int64_t)blockIdx.x * PTS;
+    const int64_t p = p0 + t;
+    const int npts = (int)((n - p0) < PTS ? (n - p0) : PTS);
+    double* acts = sm + s.act_off;  // layer 0 rows: in_dim; layer l>=1 rows: wp each
+    auto act = [&](int l) { return acts + (l == 0 ? 0 : (d.in_dim + (l - 1) * d.wp)) * PS; };
+    load_input(d, X, centroid, load_factor, p, n, act(0), t);
+    __syncthreads();
+    for (int l = 0; l < d.L; ++l)
+        hidden_layer(sm + s.w_off[l], sm + s.b_off[l], l == 0 ? d.in_dim : d.w, d.wp, act(l), act(l + 1), t);
+    double z = sm[s.bo_off];
+    for (int i = 0; i < d.w; ++i) z = fma(sm[s.wo_off + i], act(d.L)[i * PS + t], z);
+    double dz = 0.0;
+    if (p < n) dz = (MODE == 0 ? g_out[p] : 1.0) * pf_mlp_output_grad(z, scale, positive);
+    sm[s.dz_off + t] = dz;
+    double* D = sm + s.delta_off;
+    double* Dn = D + d.wp * PS;
+    // delta of the last hidden layer
+    for (int o = 0; o < d.wp; ++o) {
+        const double a = act(d.L)[o * PS + t];
+        D[o * PS + t] = sm[s.wo_off + o] * dz * (1.0 - a * a);
+    }
+    __syncthreads();
+
+    double* gdst = MODE == 0 ? dst + (int64_t)blockIdx.x * d.n_params : nullptr;
+    // output layer parameters
+    for (int q = threadIdx.x; q <= d.w; q += blockDim.x) {
+        if (MODE == 0) {
+            double acc = 0.0;
+            if (q < d.w)
+                for (int tt = 0; tt < npts; ++tt) acc = fma(sm[s.dz_off + tt], act(d.L)[q * PS + tt], acc);
+            else
+                for (int tt = 0; tt < npts; ++tt) acc += sm[s.dz_off + tt];
+            gdst[(q < d.w ? d.w_off[d.L] + q : d.b_off[d.L])] = acc;
+        }
+    }
+    if (MODE == 1) {
+        for (int tt = 0; tt < npts; ++tt) {
+            double* row = dst + (p0 + tt) * d.n_params;
+            for (int q = threadIdx.x; q <= d.w; q += blockDim.x)
+                row[q < d.w ? d.w_off[d.L] + q : d.b_off[d.L]] =
+                    q < d.w ? sm[s.dz_off + tt] * act(d.L)[q * PS + tt] : sm[s.dz_off + tt];
+        }
+    }
+    // hidden layers, last to first
+    for (int l = d.L - 1; l >= 0; --l) {
+        const int in = l == 0 ? d.in_dim : d.w;
+        const double* a_in = act(l);
+        const int npair = d.w * in;
+        if (MODE == 0) {
+            for (int q = threadIdx.x; q < npair + d.w; q += blockDim.x) {
+                double acc = 0.0;
+                if (q < npair) {
+                    const int o = q / in, i = q % in;
+                    for (int tt = 0; tt < npts; ++tt) acc = fma(D[o * PS + tt], a_in[i * PS + tt], acc);
+                    gdst[d.w_off[l] + q] = acc;
+                } else {
+                    const int o = q - npair;
+                    for (int tt = 0; tt < npts; ++tt) acc += D[o * PS + tt];
+                    gdst[d.b_off[l] + o] = acc;
+                }
+            }
+        } else {
+            for (int tt = 0; tt < npts; ++tt) {
+                double* row = dst + (p0 + tt) * d.n_params;
+                for (int q = threadIdx.x; q < npair + d.w; q += blockDim.x) {
+                    if (q < npair) {
+                        const int o = q / in, i = q % in;
+                        row[d.w_off[l] + q] = D[o * PS + tt] * a_in[i * PS + tt];
+                    } else {
+                        row[d.b_off[l] + (q - npair)] = D[(q - npair) * PS + tt];
+                    }
+                }
+            }
+        }
+        if (l > 0) {
+            // delta of layer l-1's output: Dn[i][t] = (sum_o W_l[o][i] D[o][t]) (1 - a^2)
+            const double* Wt = sm + s.w_off[l];  // [in][wp]
+            for (int i = 0; i < d.w; ++i) {
+                double acc = 0.0;
+                for (int o = 0; o < d.w; ++o) acc = fma(Wt[i * d.wp + o], D[o * PS + t], acc);
+                const double a = a_in[i * PS + t];
+                Dn[i * PS + t] = acc * (1.0 - a * a);
+            }
+            for (int i = d.w; i < d.wp; ++i) Dn[i * PS + t] = 0.0;
+            __syncthreads();
+            double* tmp = D;
+            D = Dn;
+            Dn = tmp;
+        }
+    }
+}
+
+__global__ void reduce_rows_kernel(const double* __restrict__ part, int64_t rows, int64_t cols,
+                                   double* __restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double acc = 0.0;
+    for (int64_t r = 0; r < rows; ++r) acc += part[r * cols + c];
+    out[c] = acc;
+}
+
+}  // namespace
+
+int pf_mlp_make_desc(int input_dim, int hidden_layers, int width, PfMlpDesc* d) {
+    PF_REQUIRE(input_dim >= 1 && input_dim <= 16, "MLP input_dim must be in [1,16], got %d", input_dim);
+    PF_REQUIRE(hidden_layers >= 1 && hidden_layers <= PF_MLP_MAX_LAYERS, "MLP hidden_layers must be in [1,%d]",
+               PF_MLP_MAX_LAYERS);
+    PF_REQUIRE(width >= 1 && width <= 128, "MLP width must be in [1,128], got %d", width);
+    d->in_dim = input_dim;
+    d->L = hidden_layers;
+    d->w = width;
+    d->wp = (width + 3) & ~3;
+    int off = 0;
+    for (int l = 0; l < hidden_layers; ++l) {
+        const int in = l == 0 ? input_dim : width;
+        d->w_off[l] = off;
+        off += width * in;
+        d->b_off[l] = off;
+        off += width;
+    }
+    d->w_off[hidden_layers] = off;
+    off += width;
+    d->b_off[hidden_layers] = off;
+    off += 1;
+    d->n_params = off;
+    return PF_OK;
+}
+
+extern "C" int64_t pf_mlp_num_params(int input_dim, int hidden_layers, int width) {
+    PfMlpDesc d;
+    if (pf_mlp_make_desc(input_dim, hidden_layers, width, &d) != PF_OK) return -1;
+    return d.n_params;
+}
+
+static int mlp_common(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta, int64_t n,
+                      const double* X, PfMlpDesc* d, const double** centroid) {
+    int rc = pf_mlp_make_desc(input_dim, hidden_layers, width, d);
+    if (rc) return rc;
+    PF_REQUIRE(theta != nullptr, "theta is NULL");
+    PF_REQUIRE(n >= 0, "n must be >= 0");
+    *centroid = nullptr;
+    if (X == nullptr) {
+        PF_REQUIRE(plan != nullptr, "X is NULL and no plan given");
+        rc = pf_plan_activate(plan);
+        if (rc) return rc;
+        PF_REQUIRE(n == plan->nelem, "centroid mode needs n == nelem");
+        PF_REQUIRE(input_dim == plan->dim + 1,
+                   "network input_dim %d does not match [load_factor, centroid] = %d inputs (fem/properties.py:116-125)",
+                   input_dim, plan->dim + 1);
+        *centroid = plan->d_centroid;
+    } else if (plan) {
+        rc = pf_plan_activate(plan);
+        if (rc) return rc;
+    }
+    return PF_OK;
+}
+
+template <typename Kernel>
+static int set_smem(Kernel k, size_t bytes) {
+    PF_REQUIRE(bytes <= 220 * 1024, "network too large for the shared-memory MLP kernels (%zu bytes)", bytes);
+    if (bytes > 48 * 1024) PF_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PF_OK;
+}
+
+extern "C" int pf_mlp_forward(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta,
+                              int64_t n, const double* X, double load_factor, double scale, int enforce_positive,
+                              double* out, void* stream) {
+    PfMlpDesc d;
+    const double* cen;
+    int rc = mlp_common(plan, input_dim, hidden_layers, width, theta, n, X, &d, &cen);
+    if (rc) return rc;
+    PF_REQUIRE(out != nullptr, "out is NULL");
+    if (n == 0) return PF_OK;
+    const size_t smem = (size_t)smem_plan(d, false).total * sizeof(double);
+    if ((rc = set_smem(mlp_forward_kernel, smem))) return rc;
+    mlp_forward_kernel<<<(unsigned)((n + PTS - 1) / PTS), PTS, smem, pf_stream_of(stream)>>>(
+        d, theta, n, X, cen, load_factor, scale, enforce_positive, out);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return PF_OK;
+}
+
+// scratch for cross-CTA partial gradients when no plan is available
+static thread_local double* g_scratch = nullptr;
+static thread_local size_t g_scratch_bytes = 0;
+
+static int scratch(pf_plan* plan, size_t bytes, double** out) {
+    if (plan) {
+        int rc = pf_plan_reserve_work(plan, bytes);
+        *out = plan->d_work;
+        return rc;
+    }
+    if (bytes > g_scratch_bytes) {
+        if (g_scratch) PF_CUDA_CHECK(cudaFree(g_scratch));
+        g_scratch = nullptr;
+        g_scratch_bytes = 0;
+        PF_CUDA_CHECK(cudaMalloc((void**)&g_scratch, bytes));
+        g_scratch_bytes = bytes;
+    }
+    *out = g_scratch;
+    return PF_OK;
+}
+
+extern "C" int pf_mlp_backward(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta,
+                               int64_t n, const double* X, double load_factor, double scale, int enforce_positive,
+                               const double* g_out, double* g_theta, void* stream) {
+    PfMlpDesc d;
+    const double* cen;
+    int rc = mlp_common(plan, input_dim, hidden_layers, width, theta, n, X, &d, &cen);
+    if (rc) return rc;
+    PF_REQUIRE(g_out != nullptr && g_theta != nullptr, "g_out/g_theta is NULL");
+    cudaStream_t st = pf_stream_of(stream);
+    if (n == 0) {
+        PF_CUDA_CHECK(cudaMemsetAsync(g_theta, 0, d.n_params * sizeof(double), st));
+        return PF_OK;
+    }
+    const size_t smem = (size_t)smem_plan(d, true).total * sizeof(double);
+    if ((rc = set_smem(mlp_backward_kernel<0>, smem))) return rc;
+    const unsigned blocks = (unsigned)((n + PTS - 1) / PTS);
+    double* part = g_theta;
+    if (blocks > 1 && (rc = scratch(plan, (size_t)blocks * d.n_params * sizeof(double), &part))) return rc;
+    mlp_backward_kernel<0><<<blocks, PTS, smem, st>>>(d, theta, n, X, cen, load_factor, scale, enforce_positive,
+                                                      g_out, part);
+    PF_CUDA_CHECK(cudaGetLastError());
+    if (blocks > 1) {
+        reduce_rows_kernel<<<(d.n_params + 127) / 128, 128, 0, st>>>(part, blocks, d.n_params, g_theta);
+        PF_CUDA_CHECK(cudaGetLastError());
+    }
+    return PF_OK;
+}
+
+extern "C" int pf_mlp_param_jacobian(pf_plan* plan, int input_dim, int hidden_layers, int width,
+                                     const double* theta, int64_t n, const double* X, double load_factor,
+                                     double scale, int enforce_positive, double* jac, void* stream) {
+    PfMlpDesc d;
+    const double* cen;
+    int rc = mlp_common(plan, input_dim, hidden_layers, width, theta, n, X, &d, &cen);
+    if (rc) return rc;
+    PF_REQUIRE(jac != nullptr, "jac is NULL");
+    if (n == 0) return PF_OK;
+    const size_t smem = (size_t)smem_plan(d, true).total * sizeof(double);
+    if ((rc = set_smem(mlp_backward_kernel<1>, smem))) return rc;
+    mlp_backward_kernel<1><<<(unsigned)((n + PTS - 1) / PTS), PTS, smem, pf_stream_of(stream)>>>(
+        d, theta, n, X, cen, load_factor, scale, enforce_positive, nullptr, jac);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return PF_OK;
+}
