@@ -11,6 +11,10 @@
 // mesh indices / geometry are warp-uniform broadcast loads amortised over the
 // batch.  Each E/A row is read from DRAM once; its second use (from the
 // element's other end node) hits L1/L2.
+#include <algorithm>
+#include <cstdlib>
+
+#include "pf_element.cuh"
 #include "pf_internal.h"
 
 namespace {
@@ -33,7 +37,8 @@ struct GatherArgs {
     double* __restrict__ half_sq_part; // [gridDim.x][B] partial sums of 0.5 r^2
     unsigned long long* __restrict__ max_strain_bits;  // [B]
     int64_t nnode;
-    int64_t B;
+    int64_t B;            // problems covered by this launch
+    int64_t ldb;          // row stride of the batched arrays
     int64_t mat_stride;   // B when per-problem materials, 0 when shared
     int64_t mat_bmul;     // 1 when per-problem, 0 when shared
     int64_t fext_stride;  // B or 1
@@ -44,14 +49,14 @@ struct GatherArgs {
 
 enum { MODE_FORCE = 0, MODE_MATVEC = 1 };
 
-template <int DIM>
-struct Vec {
+// scalar (one problem) node vector, used by the element-centric kernels
+struct Vec2 {
     double x, y;
 };
 
 template <int DIM>
-__device__ __forceinline__ Vec<DIM> load_vec(const double* __restrict__ p, int64_t node, int64_t B, int64_t b) {
-    Vec<DIM> r;
+__device__ __forceinline__ Vec2 load_vec2(const double* __restrict__ p, int64_t node, int64_t B, int64_t b) {
+    Vec2 r;
     if (DIM == 2) {
         r.x = __ldg(p + (2 * node) * B + b);
         r.y = __ldg(p + (2 * node + 1) * B + b);
@@ -62,34 +67,68 @@ __device__ __forceinline__ Vec<DIM> load_vec(const double* __restrict__ p, int64
     return r;
 }
 
-// Contribution of one incident element to the owning node's force (or K v).
+// VEC consecutive problems of one row, loaded with a single 8*VEC-byte access.
+template <int VEC>
+struct Pack {
+    double v[VEC];
+};
+
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> load_pack(const double* __restrict__ p) {
+    Pack<VEC> r;
+    if (VEC == 2) {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+        r.v[0] = t.x;
+        r.v[VEC - 1] = t.y;
+    } else {
+        r.v[0] = __ldg(p);
+    }
+    return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_pack(double* __restrict__ p, const Pack<VEC>& r) {
+    if (VEC == 2)
+        *reinterpret_cast<double2*>(p) = make_double2(r.v[0], r.v[VEC - 1]);
+    else
+        p[0] = r.v[0];
+}
+
+template <int DIM, int VEC>
+struct Vec {
+    Pack<VEC> x, y;
+};
+
+template <int DIM, int VEC>
+__device__ __forceinline__ Vec<DIM, VEC> load_vec(const double* __restrict__ p, int64_t node, int64_t B, int64_t b) {
+    Vec<DIM, VEC> r;
+    if (DIM == 2) {
+        r.x = load_pack<VEC>(p + (2 * node) * B + b);
+        r.y = load_pack<VEC>(p + (2 * node + 1) * B + b);
+    } else {
+        r.x = load_pack<VEC>(p + node * B + b);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) r.y.v[i] = 0.0;
+    }
+    return r;
+}
+
+// Contribution of one incident element to the owning node's force (or K v), one problem.
 template <int DIM, int KIND, int MODE>
-__device__ __forceinline__ void incidence(double Ee, double Ae, const double4& geo, const double4& xy,
-                                          const Vec<DIM>& us, const Vec<DIM>& uo, const Vec<DIM>& vs,
-                                          const Vec<DIM>& vo, double& fx, double& fy, double& eps_abs) {
+__device__ __forceinline__ void incidence(double Ee, double Ae, const double4& geo, const double4& xy, double usx,
+                                          double usy, double uox, double uoy, double vsx, double vsy, double vox,
+                                          double voy, double& fx, double& fy, double& eps_abs) {
     const double ea = Ee * Ae;
     if (KIND == PF_ELEM_LINEAR || DIM == 1) {
-        // fe = ke @ u_e with ke = (EA/l0) * d (x) d, d = [c, s, -c, -s]
-        // (fem/element.py:80-100): row of the owning node = k * (d . (u_self - u_other)) * (c, s)
-        const double k = ea * geo.z;
-        const Vec<DIM>& a = (MODE == MODE_MATVEC) ? vs : us;
-        const Vec<DIM>& o = (MODE == MODE_MATVEC) ? vo : uo;
-        if (DIM == 2) {
-            const double axial = geo.x * (a.x - o.x) + geo.y * (a.y - o.y);
-            const double t = k * axial;
-            fx += t * geo.x;
-            fy += t * geo.y;
-            eps_abs = fmax(eps_abs, fabs(axial * geo.z));
-        } else {
-            const double du = a.x - o.x;
-            fx += k * du;
-            eps_abs = fmax(eps_abs, fabs(du * geo.z));
-        }
+        const double ax = (MODE == MODE_MATVEC) ? vsx : usx, ay = (MODE == MODE_MATVEC) ? vsy : usy;
+        const double ox = (MODE == MODE_MATVEC) ? vox : uox, oy = (MODE == MODE_MATVEC) ? voy : uoy;
+        const double eps = pf_linear_incidence<DIM>(Ee, Ae, geo, ax, ay, ox, oy, fx, fy);
+        if (MODE == MODE_FORCE) eps_abs = fmax(eps_abs, eps);
     } else {
         // Green-Lagrange, verbatim fem/element.py:119-131 seen from the owning node:
         // d = (x_o + u_o) - (x_s + u_s), e = (l^2 - l0^2) / (2 l0^2)
-        const double dx = (xy.x + uo.x) - (xy.z + us.x);
-        const double dy = (xy.y + uo.y) - (xy.w + us.y);
+        const double dx = (xy.x + uox) - (xy.z + usx);
+        const double dy = (xy.y + uoy) - (xy.w + usy);
         const double l0 = geo.w;
         const double e = (dx * dx + dy * dy - l0 * l0) * (0.5 * geo.z * geo.z);
         if (MODE == MODE_FORCE) {
@@ -100,7 +139,7 @@ __device__ __forceinline__ void incidence(double Ee, double Ae, const double4& g
         } else {
             // ke = EA/l0^3 d0 (x) d0 + EA/l0 e d (x) d ; row of owning node acts on (v_s - v_o)
             const double dx0 = xy.x - xy.z, dy0 = xy.y - xy.w;
-            const double wx = vs.x - vo.x, wy = vs.y - vo.y;
+            const double wx = vsx - vox, wy = vsy - voy;
             const double a = ea * geo.z * geo.z * geo.z * (dx0 * wx + dy0 * wy);
             const double b = ea * geo.z * e * (dx * wx + dy * wy);
             fx += a * dx0 + b * dx;
@@ -109,84 +148,167 @@ __device__ __forceinline__ void incidence(double Ee, double Ae, const double4& g
     }
 }
 
-template <int DIM, int KIND, int MODE>
+// Incidence records of the CTA's node tile are staged in shared memory first
+// (one coalesced cooperative copy), so the data loads below do not wait on a
+// dependent index load from L2/DRAM; the loads of up to UD incident elements
+// (4 rows each) are issued back to back before the first use, and every lane
+// moves VEC problems per access (LDG.128 for VEC = 2): the SM's budget of
+// outstanding load requests, not DRAM, is what limits bytes in flight here.
+constexpr int kIncCap = 192;  // staged incidences per CTA (more are read from global)
+
+template <int DIM, int KIND, int MODE, int UD, int VEC>
 __global__ void __launch_bounds__(kMaxBlockThreads) node_gather_kernel(GatherArgs a) {
-    const int64_t b = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-    const bool b_ok = b < a.B;
+    __shared__ PfIncidence s_inc[kIncCap];
+    __shared__ double4 s_geo[kIncCap];
+    __shared__ double4 s_xy[(KIND == PF_ELEM_GREEN_LAGRANGE && DIM == 2) ? kIncCap : 1];
+    __shared__ int s_ptr[kMaxBlockThreads + 1];
+    constexpr bool kNeedU = (KIND != PF_ELEM_LINEAR && DIM == 2) || MODE == MODE_FORCE;
+    constexpr bool kNeedV = MODE == MODE_MATVEC;
+    constexpr bool kNeedXY = KIND == PF_ELEM_GREEN_LAGRANGE && DIM == 2;
+
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    const int tile_nodes = blockDim.y * a.nodes_per_thread;
+    const int64_t tile0 = (int64_t)blockIdx.x * tile_nodes;
+    const int tile_n = (int)(a.nnode - tile0 < tile_nodes ? a.nnode - tile0 : tile_nodes);
+    for (int i = tid; i <= tile_n; i += nthreads) s_ptr[i] = __ldg(a.inc_ptr + tile0 + i);
+    __syncthreads();
+    const int kbase = s_ptr[0];
+    const int kstaged = min(s_ptr[tile_n] - kbase, kIncCap);
+    for (int i = tid; i < kstaged; i += nthreads) {
+        s_inc[i] = a.inc[kbase + i];
+        s_geo[i] = a.inc_geo[kbase + i];
+        if (kNeedXY) s_xy[i] = a.inc_xy[kbase + i];
+    }
+    __syncthreads();
+
+    const int64_t b = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * VEC;
+    const bool b_ok = b < a.B;  // B is a multiple of VEC (checked by the launcher)
     const int64_t bb = b_ok ? b : 0;
-    const int64_t node0 = ((int64_t)blockIdx.x * blockDim.y + threadIdx.y) * a.nodes_per_thread;
-    double sq = 0.0, eps_abs = 0.0;
+    const double* __restrict__ Eb = a.E + bb * a.mat_bmul;
+    const double* __restrict__ Ab = a.A + bb * a.mat_bmul;
+    double sq[VEC], eps_abs[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) sq[i] = eps_abs[i] = 0.0;
 
     for (int t = 0; t < a.nodes_per_thread; ++t) {
-        const int64_t n = node0 + t;
-        if (n >= a.nnode) break;
-        const int k0 = __ldg(a.inc_ptr + n), k1 = __ldg(a.inc_ptr + n + 1);
-        Vec<DIM> us = {0.0, 0.0}, vs = {0.0, 0.0};
-        if (KIND != PF_ELEM_LINEAR || MODE == MODE_FORCE) us = load_vec<DIM>(a.u, n, a.B, bb);
-        if (MODE == MODE_MATVEC) vs = load_vec<DIM>(a.v, n, a.B, bb);
-        double fx = 0.0, fy = 0.0;
-#pragma unroll 4
-        for (int k = k0; k < k1; ++k) {
-            const PfIncidence inc = a.inc[k];
-            const double4 geo = a.inc_geo[k];
-            double4 xy = make_double4(0, 0, 0, 0);
-            if (KIND == PF_ELEM_GREEN_LAGRANGE && DIM == 2) xy = a.inc_xy[k];
-            const double Ee = __ldg(a.E + (int64_t)inc.elem * a.mat_stride + bb * a.mat_bmul);
-            const double Ae = __ldg(a.A + (int64_t)inc.elem * a.mat_stride + bb * a.mat_bmul);
-            Vec<DIM> uo = {0.0, 0.0}, vo = {0.0, 0.0};
-            if (KIND != PF_ELEM_LINEAR || MODE == MODE_FORCE) uo = load_vec<DIM>(a.u, inc.nbr, a.B, bb);
-            if (MODE == MODE_MATVEC) vo = load_vec<DIM>(a.v, inc.nbr, a.B, bb);
-            incidence<DIM, KIND, MODE>(Ee, Ae, geo, xy, us, uo, vs, vo, fx, fy, eps_abs);
+        const int ln = threadIdx.y * a.nodes_per_thread + t;
+        if (ln >= tile_n) break;
+        const int64_t n = tile0 + ln;
+        const int k0 = s_ptr[ln] - kbase, k1 = s_ptr[ln + 1] - kbase;
+        Vec<DIM, VEC> us, vs;
+        if (kNeedU) us = load_vec<DIM, VEC>(a.u, n, a.ldb, bb);
+        if (kNeedV) vs = load_vec<DIM, VEC>(a.v, n, a.ldb, bb);
+        double fx[VEC], fy[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) fx[i] = fy[i] = 0.0;
+        for (int kb = k0; kb < k1; kb += UD) {
+            Pack<VEC> Ee[UD], Ae[UD];
+            Vec<DIM, VEC> uo[UD], vo[UD];
+#pragma unroll
+            for (int j = 0; j < UD; ++j) {
+                const int k = kb + j;
+                if (k < k1) {
+                    const PfIncidence inc = k < kIncCap ? s_inc[k] : a.inc[kbase + k];
+                    const int64_t eo = (int64_t)inc.elem * a.mat_stride;
+                    if (a.mat_bmul) {
+                        Ee[j] = load_pack<VEC>(Eb + eo);
+                        Ae[j] = load_pack<VEC>(Ab + eo);
+                    } else {  // materials shared by all problems: one scalar per element
+                        const double e1 = __ldg(a.E + eo), a1 = __ldg(a.A + eo);
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) {
+                            Ee[j].v[i] = e1;
+                            Ae[j].v[i] = a1;
+                        }
+                    }
+                    if (kNeedU) uo[j] = load_vec<DIM, VEC>(a.u, inc.nbr, a.ldb, bb);
+                    if (kNeedV) vo[j] = load_vec<DIM, VEC>(a.v, inc.nbr, a.ldb, bb);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UD; ++j) {
+                const int k = kb + j;
+                if (k < k1) {
+                    const double4 geo = k < kIncCap ? s_geo[k] : a.inc_geo[kbase + k];
+                    double4 xy = make_double4(0, 0, 0, 0);
+                    if (kNeedXY) xy = k < kIncCap ? s_xy[k] : a.inc_xy[kbase + k];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i)
+                        incidence<DIM, KIND, MODE>(Ee[j].v[i], Ae[j].v[i], geo, xy, kNeedU ? us.x.v[i] : 0.0,
+                                                   kNeedU ? us.y.v[i] : 0.0, kNeedU ? uo[j].x.v[i] : 0.0,
+                                                   kNeedU ? uo[j].y.v[i] : 0.0, kNeedV ? vs.x.v[i] : 0.0,
+                                                   kNeedV ? vs.y.v[i] : 0.0, kNeedV ? vo[j].x.v[i] : 0.0,
+                                                   kNeedV ? vo[j].y.v[i] : 0.0, fx[i], fy[i], eps_abs[i]);
+                }
+            }
         }
         if (b_ok) {
             const int64_t d0 = (DIM == 2) ? 2 * n : n;
             if (a.f_out) {
-                a.f_out[d0 * a.B + b] = fx;
-                if (DIM == 2) a.f_out[(d0 + 1) * a.B + b] = fy;
+                Pack<VEC> px, py;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    px.v[i] = fx[i];
+                    py.v[i] = fy[i];
+                }
+                store_pack<VEC>(a.f_out + d0 * a.ldb + b, px);
+                if (DIM == 2) store_pack<VEC>(a.f_out + (d0 + 1) * a.ldb + b, py);
             }
             if (MODE == MODE_FORCE && (a.r_out || a.half_sq_part)) {
-                double rx = 0.0, ry = 0.0;
-                if (a.dof_free[d0]) rx = fx - a.load_factor * __ldg(a.f_ext + d0 * a.fext_stride + b * a.fext_bmul);
-                if (DIM == 2 && a.dof_free[d0 + 1])
-                    ry = fy - a.load_factor * __ldg(a.f_ext + (d0 + 1) * a.fext_stride + b * a.fext_bmul);
-                if (a.r_out) {
-                    a.r_out[d0 * a.B + b] = rx;
-                    if (DIM == 2) a.r_out[(d0 + 1) * a.B + b] = ry;
+                Pack<VEC> rx, ry;
+                const bool free_x = a.dof_free[d0], free_y = DIM == 2 ? a.dof_free[d0 + 1] : false;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    rx.v[i] = ry.v[i] = 0.0;
+                    if (free_x) rx.v[i] = fx[i] - a.load_factor * __ldg(a.f_ext + d0 * a.fext_stride + (b + i) * a.fext_bmul);
+                    if (free_y)
+                        ry.v[i] = fy[i] - a.load_factor * __ldg(a.f_ext + (d0 + 1) * a.fext_stride + (b + i) * a.fext_bmul);
+                    sq[i] += rx.v[i] * rx.v[i];  // node order inside a thread is ascending
+                    sq[i] += ry.v[i] * ry.v[i];
                 }
-                sq += rx * rx;  // node order inside a thread is ascending
-                sq += ry * ry;
+                if (a.r_out) {
+                    store_pack<VEC>(a.r_out + d0 * a.ldb + b, rx);
+                    if (DIM == 2) store_pack<VEC>(a.r_out + (d0 + 1) * a.ldb + b, ry);
+                }
             }
         }
     }
 
     if (MODE == MODE_FORCE && (a.half_sq_part || a.max_strain_bits)) {
         // deterministic block reduction over threadIdx.y for each problem column
-        __shared__ double s_sq[kMaxBlockThreads];
-        __shared__ double s_eps[kMaxBlockThreads];
-        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-        s_sq[tid] = sq;
-        s_eps[tid] = eps_abs;
+        __shared__ double s_sq[kMaxBlockThreads * VEC];
+        __shared__ double s_eps[kMaxBlockThreads * VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            s_sq[tid * VEC + i] = sq[i];
+            s_eps[tid * VEC + i] = eps_abs[i];
+        }
         __syncthreads();
         if (threadIdx.y == 0 && b_ok) {
-            double acc = 0.0, m = 0.0;
-            for (int y = 0; y < (int)blockDim.y; ++y) {
-                acc += s_sq[y * blockDim.x + threadIdx.x];
-                m = fmax(m, s_eps[y * blockDim.x + threadIdx.x]);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                double acc = 0.0, m = 0.0;
+                for (int y = 0; y < (int)blockDim.y; ++y) {
+                    acc += s_sq[(y * blockDim.x + threadIdx.x) * VEC + i];
+                    m = fmax(m, s_eps[(y * blockDim.x + threadIdx.x) * VEC + i]);
+                }
+                if (a.half_sq_part) a.half_sq_part[(int64_t)blockIdx.x * a.ldb + b + i] = acc;
+                // non-negative doubles order like their bit patterns; max is exact and order independent
+                if (a.max_strain_bits)
+                    atomicMax(a.max_strain_bits + b + i, (unsigned long long)__double_as_longlong(m));
             }
-            if (a.half_sq_part) a.half_sq_part[(int64_t)blockIdx.x * a.B + b] = acc;
-            // non-negative doubles order like their bit patterns; max is exact and order independent
-            if (a.max_strain_bits) atomicMax(a.max_strain_bits + b, (unsigned long long)__double_as_longlong(m));
         }
     }
 }
 
 // out[b] = scale * sum_rows part[row][b], rows added in ascending order (deterministic).
-__global__ void column_sum_kernel(const double* __restrict__ part, int64_t rows, int64_t B, double scale,
-                                  double* __restrict__ out) {
+__global__ void column_sum_kernel(const double* __restrict__ part, int64_t rows, int64_t ld, int64_t B,
+                                  double scale, double* __restrict__ out) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     double acc = 0.0;
-    for (int64_t r = 0; r < rows; ++r) acc += part[r * B + b];
+    for (int64_t r = 0; r < rows; ++r) acc += part[r * ld + b];
     out[b] = scale * acc;
 }
 
@@ -213,8 +335,8 @@ __global__ void __launch_bounds__(kMaxBlockThreads) material_vjp_kernel(VjpArgs 
     if (b >= a.B || e >= a.nelem) return;
     const int2 c = a.conn[e];
     const double4 geo = a.elem_geo[e];
-    const Vec<DIM> ui = load_vec<DIM>(a.u, c.x, a.B, b), uj = load_vec<DIM>(a.u, c.y, a.B, b);
-    const Vec<DIM> gi = load_vec<DIM>(a.g, c.x, a.B, b), gj = load_vec<DIM>(a.g, c.y, a.B, b);
+    const Vec2 ui = load_vec2<DIM>(a.u, c.x, a.B, b), uj = load_vec2<DIM>(a.u, c.y, a.B, b);
+    const Vec2 gi = load_vec2<DIM>(a.g, c.x, a.B, b), gj = load_vec2<DIM>(a.g, c.y, a.B, b);
     double gh;  // <g_e, f_e / (E A)>
     if (KIND == PF_ELEM_LINEAR || DIM == 1) {
         if (DIM == 2) {
@@ -260,8 +382,8 @@ __global__ void __launch_bounds__(kMaxBlockThreads) tangent_bsr_kernel(TangentAr
     const int64_t n = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
     if (b >= a.B || n >= a.nnode) return;
     const int k0 = a.inc_ptr[n], k1 = a.inc_ptr[n + 1];
-    Vec<DIM> us = {0.0, 0.0};
-    if (KIND != PF_ELEM_LINEAR && DIM == 2) us = load_vec<DIM>(a.u, n, a.B, b);
+    Vec2 us = {0.0, 0.0};
+    if (KIND != PF_ELEM_LINEAR && DIM == 2) us = load_vec2<DIM>(a.u, n, a.B, b);
     double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;
     for (int k = k0; k < k1; ++k) {
         const PfIncidence inc = a.inc[k];
@@ -278,7 +400,7 @@ __global__ void __launch_bounds__(kMaxBlockThreads) tangent_bsr_kernel(TangentAr
             if (DIM == 1) k00 = kk;
         } else {
             const double4 xy = a.inc_xy[k];
-            const Vec<DIM> uo = load_vec<DIM>(a.u, inc.nbr, a.B, b);
+            const Vec2 uo = load_vec2<DIM>(a.u, inc.nbr, a.B, b);
             const double dx0 = xy.x - xy.z, dy0 = xy.y - xy.w;
             const double dx = (xy.x + uo.x) - (xy.z + us.x);
             const double dy = (xy.y + uo.y) - (xy.w + us.y);
@@ -373,67 +495,135 @@ static int check_common(pf_plan* plan, int kind, int64_t B, const double* E, con
         }                                                              \
     } while (0)
 
-static int launch_gather(pf_plan* plan, int kind, int mode, int64_t B, const double* u, const double* v,
-                         const double* E, const double* A, int mat_batched, double* f_out, const double* f_ext,
-                         int fext_batched, double load_factor, double* r, double* half_sq, double* max_strain,
-                         cudaStream_t st) {
+// Generic node gather on the column range [b0, b0 + nb) of arrays whose row stride is ldb.
+static int launch_gather_generic(pf_plan* plan, int kind, int mode, int64_t ldb, int64_t b0, int64_t nb,
+                                 const double* u, const double* v, const double* E, const double* A,
+                                 int mat_batched, double* f_out, const double* f_ext, int fext_batched,
+                                 double load_factor, double* r, double* half_sq, double* max_strain,
+                                 cudaStream_t st) {
+    auto off = [&](const double* q, bool batched) { return (q && batched) ? q + b0 : q; };
+    auto offw = [&](double* q) { return q ? q + b0 : q; };
     GatherArgs a{};
     a.inc_ptr = plan->d_inc_ptr;
     a.inc = plan->d_inc;
     a.inc_geo = plan->d_inc_geo;
     a.inc_xy = plan->d_inc_xy;
     a.dof_free = plan->d_dof_free;
-    a.u = u;
-    a.v = v;
-    a.E = E;
-    a.A = A;
-    a.f_ext = f_ext;
-    a.f_out = f_out;
-    a.r_out = r;
+    a.u = off(u, true);
+    a.v = off(v, true);
+    a.E = off(E, mat_batched);
+    a.A = off(A, mat_batched);
+    a.f_ext = off(f_ext, fext_batched);
+    a.f_out = offw(f_out);
+    a.r_out = offw(r);
     a.nnode = plan->nnode;
-    a.B = B;
-    a.mat_stride = mat_batched ? B : 1;
+    a.B = nb;
+    a.ldb = ldb;
+    a.mat_stride = mat_batched ? ldb : 1;
     a.mat_bmul = mat_batched ? 1 : 0;
-    a.fext_stride = fext_batched ? B : 1;
+    a.fext_stride = fext_batched ? ldb : 1;
     a.fext_bmul = fext_batched ? 1 : 0;
     a.load_factor = load_factor;
 
+    // tuning knobs (environment, read once): lanes per CTA row, nodes per thread, problems per lane
+    static const int env_bx = getenv("PF_GATHER_BX") ? atoi(getenv("PF_GATHER_BX")) : 0;
+    static const int env_npt = getenv("PF_GATHER_NPT") ? atoi(getenv("PF_GATHER_NPT")) : 0;
+    static const int env_vec = getenv("PF_GATHER_VEC") ? atoi(getenv("PF_GATHER_VEC")) : 0;
+    static const int env_ud = getenv("PF_GATHER_UD") ? atoi(getenv("PF_GATHER_UD")) : 0;
+    static const int env_threads = getenv("PF_GATHER_THREADS") ? atoi(getenv("PF_GATHER_THREADS")) : 0;
+    // two problems per lane (128-bit accesses) whenever the batch is wide, even and 16-byte aligned
+    auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    int vec = (nb % 2 == 0 && ldb % 2 == 0 && nb >= 64 && aligned16(a.u) && aligned16(a.v) && aligned16(a.f_out) &&
+               aligned16(a.r_out) && (!mat_batched || (aligned16(a.E) && aligned16(a.A))))
+                  ? 2
+                  : 1;
+    if (env_vec == 1) vec = 1;
+    const int64_t lanes = nb / vec;
     dim3 block;
-    pick_block(B, block);
-    // nodes per thread: keep >= ~8 blocks per SM in flight but bound the partial-sum rows
+    pick_block(lanes, block);
+    if (vec == 2) block.y = 128 / block.x > 0 ? 128 / block.x : 1;  // 154 regs/thread: 128-thread CTAs keep 3 per SM
+    if (env_bx > 0 && lanes >= env_bx) block = dim3(env_bx, kMaxBlockThreads / env_bx, 1);
+    if (env_threads > 0 && env_threads <= kMaxBlockThreads && env_threads >= (int)block.x)
+        block.y = env_threads / block.x;
+    // nodes per thread: amortise the per-CTA index staging but keep the grid large
     int npt = 1;
-    {
+    if (env_npt > 0 && (int)block.y * env_npt <= kMaxBlockThreads) {
+        npt = env_npt;
+    } else {
         const int64_t rows1 = (plan->nnode + block.y - 1) / block.y;
-        while (npt < 8 && rows1 / (npt * 2) >= (int64_t)plan->sm_count * 16) npt *= 2;
+        while (npt < 8 && (int)block.y * npt * 2 <= kMaxBlockThreads &&
+               rows1 / (npt * 2) >= (int64_t)plan->sm_count * 16)
+            npt *= 2;
     }
     a.nodes_per_thread = npt;
+    const int ud = env_ud > 0 ? env_ud : (vec == 2 ? 3 : plan->max_degree);
     const int64_t nodes_per_block = (int64_t)block.y * npt;
-    dim3 grid((unsigned)((plan->nnode + nodes_per_block - 1) / nodes_per_block), (unsigned)((B + block.x - 1) / block.x), 1);
-    PF_REQUIRE(grid.y <= 65535, "batch too large for one launch: B=%lld", (long long)B);
+    dim3 grid((unsigned)((plan->nnode + nodes_per_block - 1) / nodes_per_block),
+              (unsigned)((lanes + block.x - 1) / block.x), 1);
+    PF_REQUIRE(grid.y <= 65535, "batch too large for one launch: B=%lld", (long long)nb);
 
     if (half_sq) {
-        int rc = pf_plan_reserve_work(plan, (size_t)grid.x * B * sizeof(double));
+        int rc = pf_plan_reserve_work(plan, (size_t)grid.x * ldb * sizeof(double));
         if (rc) return rc;
-        a.half_sq_part = plan->d_work;
+        a.half_sq_part = plan->d_work + b0;
     }
-    if (max_strain) {
-        PF_CUDA_CHECK(cudaMemsetAsync(max_strain, 0, B * sizeof(double), st));
-        a.max_strain_bits = reinterpret_cast<unsigned long long*>(max_strain);
-    }
-#define PF_GATHER_CALL(D, K)                                                       \
-    do {                                                                           \
-        if (mode == MODE_FORCE)                                                    \
-            node_gather_kernel<D, K, MODE_FORCE><<<grid, block, 0, st>>>(a);       \
-        else                                                                       \
-            node_gather_kernel<D, K, MODE_MATVEC><<<grid, block, 0, st>>>(a);      \
+    if (max_strain) a.max_strain_bits = reinterpret_cast<unsigned long long*>(max_strain + b0);
+#define PF_GATHER_CALL2(D, K, M)                                                        \
+    do {                                                                                \
+        if (vec == 2) {                                                                 \
+            if (ud <= 3)                                                                \
+                node_gather_kernel<D, K, M, 3, 2><<<grid, block, 0, st>>>(a);           \
+            else                                                                        \
+                node_gather_kernel<D, K, M, 6, 2><<<grid, block, 0, st>>>(a);           \
+        } else {                                                                        \
+            if (ud <= 3)                                                                \
+                node_gather_kernel<D, K, M, 3, 1><<<grid, block, 0, st>>>(a);           \
+            else                                                                        \
+                node_gather_kernel<D, K, M, 6, 1><<<grid, block, 0, st>>>(a);           \
+        }                                                                               \
+    } while (0)
+#define PF_GATHER_CALL(D, K)                           \
+    do {                                               \
+        if (mode == MODE_FORCE)                        \
+            PF_GATHER_CALL2(D, K, MODE_FORCE);         \
+        else                                           \
+            PF_GATHER_CALL2(D, K, MODE_MATVEC);        \
     } while (0)
     PF_DISPATCH_DIM_KIND(plan, kind, PF_GATHER_CALL);
 #undef PF_GATHER_CALL
+#undef PF_GATHER_CALL2
     PF_CUDA_CHECK(cudaGetLastError());
     if (half_sq) {
-        column_sum_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(plan->d_work, grid.x, B, 0.5, half_sq);
+        column_sum_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(plan->d_work + b0, grid.x, ldb, nb, 0.5,
+                                                                        half_sq + b0);
         PF_CUDA_CHECK(cudaGetLastError());
     }
+    return PF_OK;
+}
+
+// Wide batches of the linear element go through the patch-staged kernel in
+// full 32-problem chunks; everything else (ragged tail, tiny batches,
+// Green-Lagrange) through the generic gather.  Both produce identical bits.
+static int launch_gather(pf_plan* plan, int kind, int mode, int64_t B, const double* u, const double* v,
+                         const double* E, const double* A, int mat_batched, double* f_out, const double* f_ext,
+                         int fext_batched, double load_factor, double* r, double* half_sq, double* max_strain,
+                         cudaStream_t st) {
+    if (max_strain) PF_CUDA_CHECK(cudaMemsetAsync(max_strain, 0, B * sizeof(double), st));
+    if (half_sq) {
+        // both kernels park partial sums in the plan workspace: size it once for the larger user
+        const size_t rows = std::max<size_t>(plan->patches.size(), (size_t)plan->nnode);
+        int rc = pf_plan_reserve_work(plan, rows * B * sizeof(double));
+        if (rc) return rc;
+    }
+    int64_t done = 0;
+    if (kind == PF_ELEM_LINEAR || plan->dim == 1) {
+        PfGatherCall c{mode, B, B, u, v, E, A, f_ext, mat_batched, fext_batched, load_factor, f_out, r, half_sq, max_strain};
+        int rc = pf_patch_gather(plan, c, st, &done);
+        if (rc) return rc;
+    }
+    if (done < B)
+        return launch_gather_generic(plan, kind, mode, B, done, B - done, u, v, E, A, mat_batched, f_out, f_ext,
+                                     fext_batched, load_factor, r, half_sq, max_strain, st);
     return PF_OK;
 }
 

@@ -47,6 +47,26 @@ struct PfIncidence {
     int32_t flags; // bit0: first incidence of this row that targets `slot`
 };
 
+// A patch is a compact set of <= kPatchNodes nodes (recursive coordinate
+// bisection) whose element data is staged once per CTA in shared memory.
+constexpr int kPatchNodes = 32;
+
+struct PfPatch {
+    int32_t node_off;   // into patch_nodes (owned nodes first, then halo nodes)
+    int32_t n_owned;
+    int32_t n_local;    // owned + halo
+    int32_t elem_off;   // into patch_elems
+    int32_t n_elem;     // elements incident to owned nodes (ascending element id)
+    int32_t inc_off;    // into patch_inc; patch_inc_ptr is indexed by node_off + local owned index
+    int32_t ptr_off;    // into patch_inc_ptr (n_owned + 1 entries, relative to inc_off)
+    int32_t pad;
+};
+
+struct PfPatchInc {
+    int16_t lelem;  // index into the patch's element list
+    int16_t lnbr;   // local index of the other node
+};
+
 struct pf_plan {
     int dim = 2;
     int64_t nnode = 0, nelem = 0, ndof = 0, nfree = 0, nfixed = 0, nnzb = 0, ninc = 0;
@@ -82,6 +102,19 @@ struct pf_plan {
     int32_t* d_bsr_rowptr = nullptr;    // [nnode+1]
     int32_t* d_bsr_colind = nullptr;    // [nnzb]
 
+    // patches (host + device)
+    std::vector<PfPatch> patches;
+    std::vector<int32_t> patch_nodes, patch_elems, patch_inc_ptr;
+    std::vector<PfPatchInc> patch_inc;
+    int max_patch_elems = 0, max_patch_local = 0, max_patch_inc = 0;
+    bool patch_ok = false;  // patch tables fit the shared-memory kernel
+    PfPatch* d_patches = nullptr;
+    int32_t* d_patch_nodes = nullptr;
+    int32_t* d_patch_elems = nullptr;
+    int32_t* d_patch_inc_ptr = nullptr;   // [sum(n_owned + 1)] offsets relative to the patch's inc_off
+    PfPatchInc* d_patch_inc = nullptr;
+    double4* d_patch_inc_geo = nullptr;   // {cos, sin, 1/l0, l0} per patch incidence
+
     // growable scratch for deterministic two-stage reductions
     double* d_work = nullptr;
     size_t work_bytes = 0;
@@ -93,6 +126,18 @@ struct pf_plan {
 };
 
 int pf_plan_reserve_work(pf_plan* plan, size_t bytes);
+
+// pf_patch.cu: shared-memory staged gather for wide batches (linear element).
+// Returns PF_OK and sets *handled when it ran; otherwise the caller uses the generic kernel.
+struct PfGatherCall {
+    int mode;  // 0 force/residual, 1 mat-vec
+    int64_t B, ldb;
+    const double *u, *v, *E, *A, *f_ext;
+    int mat_batched, fext_batched;
+    double load_factor;
+    double *f_out, *r_out, *half_sq, *max_strain;
+};
+int pf_patch_gather(pf_plan* plan, const PfGatherCall& c, cudaStream_t st, int64_t* columns_done);
 int pf_plan_activate(const pf_plan* plan);  // cudaSetDevice + uploaded check
 
 static inline cudaStream_t pf_stream_of(void* s) { return reinterpret_cast<cudaStream_t>(s); }

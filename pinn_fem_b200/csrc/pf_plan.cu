@@ -186,6 +186,101 @@ extern "C" int pf_plan_create(int dim, int64_t nnode, int64_t nelem, const int64
         p->elem_slots[4 * e + 2] = find(j, i);
         p->elem_slots[4 * e + 3] = find(j, j);
     }
+
+    // --- compact node patches by recursive coordinate bisection -------------------
+    // Every leaf gets <= kPatchNodes nodes; the split position follows the number
+    // of leaves each side must hold, so leaves are evenly filled.
+    {
+        std::vector<int32_t> order(nnode);
+        for (int64_t n = 0; n < nnode; ++n) order[n] = (int32_t)n;
+        struct Range { int64_t lo, hi, leaves; };
+        std::vector<Range> stack;
+        std::vector<std::pair<int64_t, int64_t>> leaves;
+        stack.push_back({0, nnode, (nnode + kPatchNodes - 1) / kPatchNodes});
+        const double* X = p->nodes.data();
+        while (!stack.empty()) {
+            Range r = stack.back();
+            stack.pop_back();
+            if (r.leaves <= 1) {
+                leaves.push_back({r.lo, r.hi});
+                continue;
+            }
+            int axis = 0;
+            if (dim == 2) {
+                double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
+                for (int64_t q = r.lo; q < r.hi; ++q)
+                    for (int a = 0; a < 2; ++a) {
+                        const double c = X[2 * order[q] + a];
+                        mn[a] = std::min(mn[a], c);
+                        mx[a] = std::max(mx[a], c);
+                    }
+                axis = (mx[1] - mn[1] > mx[0] - mn[0]) ? 1 : 0;
+            }
+            const int64_t lleaves = r.leaves / 2;
+            const int64_t mid = r.lo + (r.hi - r.lo) * lleaves / r.leaves;
+            auto key = [&](int32_t n) { return dim == 2 ? X[2 * n + axis] : X[n]; };
+            std::nth_element(order.begin() + r.lo, order.begin() + mid, order.begin() + r.hi,
+                             [&](int32_t a, int32_t b) { const double ka = key(a), kb = key(b); return ka < kb || (ka == kb && a < b); });
+            stack.push_back({mid, r.hi, r.leaves - lleaves});
+            stack.push_back({r.lo, mid, lleaves});
+        }
+        std::vector<int32_t> local_of(nnode, -1);
+        std::vector<int32_t> elem_local(nelem, -1);
+        std::vector<int32_t> touched_nodes, touched_elems;
+        for (auto& lf : leaves) {
+            if (lf.second <= lf.first) continue;
+            PfPatch pt{};
+            pt.node_off = (int32_t)p->patch_nodes.size();
+            pt.elem_off = (int32_t)p->patch_elems.size();
+            pt.inc_off = (int32_t)p->patch_inc.size();
+            pt.ptr_off = (int32_t)p->patch_inc_ptr.size();
+            std::vector<int32_t> owned(order.begin() + lf.first, order.begin() + lf.second);
+            std::sort(owned.begin(), owned.end());
+            pt.n_owned = (int32_t)owned.size();
+            touched_nodes.clear();
+            touched_elems.clear();
+            for (int32_t n : owned) {
+                local_of[n] = (int32_t)touched_nodes.size();
+                touched_nodes.push_back(n);
+            }
+            // elements incident to owned nodes, ascending id; halo nodes in first-seen order
+            for (int32_t n : owned)
+                for (int64_t k = p->inc_ptr[n]; k < p->inc_ptr[n + 1]; ++k) touched_elems.push_back((int32_t)p->inc_elem[k]);
+            std::sort(touched_elems.begin(), touched_elems.end());
+            touched_elems.erase(std::unique(touched_elems.begin(), touched_elems.end()), touched_elems.end());
+            for (size_t q = 0; q < touched_elems.size(); ++q) {
+                const int32_t el = touched_elems[q];
+                elem_local[el] = (int32_t)q;
+                for (int e2 = 0; e2 < 2; ++e2) {
+                    const int32_t n = p->conn[2 * el + e2];
+                    if (local_of[n] < 0) {
+                        local_of[n] = (int32_t)touched_nodes.size();
+                        touched_nodes.push_back(n);
+                    }
+                }
+            }
+            pt.n_local = (int32_t)touched_nodes.size();
+            pt.n_elem = (int32_t)touched_elems.size();
+            p->patch_nodes.insert(p->patch_nodes.end(), touched_nodes.begin(), touched_nodes.end());
+            p->patch_elems.insert(p->patch_elems.end(), touched_elems.begin(), touched_elems.end());
+            int32_t cnt = 0;
+            for (int32_t n : owned) {
+                p->patch_inc_ptr.push_back(cnt);
+                for (int64_t k = p->inc_ptr[n]; k < p->inc_ptr[n + 1]; ++k) {
+                    p->patch_inc.push_back(PfPatchInc{(int16_t)elem_local[p->inc_elem[k]], (int16_t)local_of[p->inc_nbr[k]]});
+                    ++cnt;
+                }
+            }
+            p->patch_inc_ptr.push_back(cnt);  // n_owned + 1 entries per patch
+            p->max_patch_elems = std::max(p->max_patch_elems, pt.n_elem);
+            p->max_patch_local = std::max(p->max_patch_local, pt.n_local);
+            p->max_patch_inc = std::max(p->max_patch_inc, cnt);
+            for (int32_t n : touched_nodes) local_of[n] = -1;
+            for (int32_t el : touched_elems) elem_local[el] = -1;
+            p->patches.push_back(pt);
+        }
+        p->patch_ok = p->max_patch_elems < 32000 && p->max_patch_local < 32000;
+    }
     *out = p;
     return PF_OK;
 }
@@ -261,6 +356,28 @@ extern "C" int pf_plan_upload(pf_plan* p, int device) {
     if ((rc = upload(&p->d_free_index, free_index))) return rc;
     if ((rc = upload(&p->d_bsr_rowptr, rowptr32))) return rc;
     if ((rc = upload(&p->d_bsr_colind, colind32))) return rc;
+    {
+        // patch tables; patch_inc_ptr of patch q starts at node_off_owned_prefix(q) + q
+        std::vector<double4> pgeo(p->patch_inc.size());
+        size_t ptr_pos = 0;
+        for (const PfPatch& pt : p->patches) {
+            for (int l = 0; l < pt.n_owned; ++l) {
+                const int32_t n = p->patch_nodes[pt.node_off + l];
+                const int32_t k0 = p->patch_inc_ptr[ptr_pos + l], k1 = p->patch_inc_ptr[ptr_pos + l + 1];
+                for (int32_t k = k0; k < k1; ++k) {
+                    const int64_t el = p->inc_elem[p->inc_ptr[n] + (k - k0)];
+                    pgeo[pt.inc_off + k] = make_double4(p->cosv[el], p->sinv[el], 1.0 / p->l0[el], p->l0[el]);
+                }
+            }
+            ptr_pos += pt.n_owned + 1;
+        }
+        if ((rc = upload(&p->d_patches, p->patches))) return rc;
+        if ((rc = upload(&p->d_patch_nodes, p->patch_nodes))) return rc;
+        if ((rc = upload(&p->d_patch_elems, p->patch_elems))) return rc;
+        if ((rc = upload(&p->d_patch_inc_ptr, p->patch_inc_ptr))) return rc;
+        if ((rc = upload(&p->d_patch_inc, p->patch_inc))) return rc;
+        if ((rc = upload(&p->d_patch_inc_geo, pgeo))) return rc;
+    }
     p->device = device;
     return PF_OK;
 }
@@ -291,7 +408,8 @@ extern "C" void pf_plan_destroy(pf_plan* p) {
         cudaSetDevice(p->device);
         void* ptrs[] = {p->d_inc_ptr, p->d_inc, p->d_inc_geo, p->d_inc_xy, p->d_diag_slot, p->d_conn,
                         p->d_elem_geo, p->d_elem_xy, p->d_centroid, p->d_dof_free, p->d_free_dofs,
-                        p->d_free_index, p->d_bsr_rowptr, p->d_bsr_colind, p->d_work};
+                        p->d_free_index, p->d_bsr_rowptr, p->d_bsr_colind, p->d_work, p->d_patches,
+                        p->d_patch_nodes, p->d_patch_elems, p->d_patch_inc_ptr, p->d_patch_inc, p->d_patch_inc_geo};
         for (void* q : ptrs)
             if (q) cudaFree(q);
         for (int s = 0; s < 3; ++s) {
