@@ -261,9 +261,11 @@ __global__ void __launch_bounds__(kMaxBlockThreads) node_gather_kernel(GatherArg
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
                     rx.v[i] = ry.v[i] = 0.0;
-                    if (free_x) rx.v[i] = fx[i] - a.load_factor * __ldg(a.f_ext + d0 * a.fext_stride + (b + i) * a.fext_bmul);
+                    // product rounded first, like the reference's f_int[free] - lambda * f_ext[free]
+                    if (free_x)
+                        rx.v[i] = __dsub_rn(fx[i], __dmul_rn(a.load_factor, __ldg(a.f_ext + d0 * a.fext_stride + (b + i) * a.fext_bmul)));
                     if (free_y)
-                        ry.v[i] = fy[i] - a.load_factor * __ldg(a.f_ext + (d0 + 1) * a.fext_stride + (b + i) * a.fext_bmul);
+                        ry.v[i] = __dsub_rn(fy[i], __dmul_rn(a.load_factor, __ldg(a.f_ext + (d0 + 1) * a.fext_stride + (b + i) * a.fext_bmul)));
                     sq[i] += rx.v[i] * rx.v[i];  // node order inside a thread is ascending
                     sq[i] += ry.v[i] * ry.v[i];
                 }
@@ -556,7 +558,7 @@ static int launch_gather_generic(pf_plan* plan, int kind, int mode, int64_t ldb,
             npt *= 2;
     }
     a.nodes_per_thread = npt;
-    const int ud = env_ud > 0 ? env_ud : (vec == 2 ? 3 : plan->max_degree);
+    const int ud = env_ud > 0 ? env_ud : 3;  // 3 incidences per load batch: best register/occupancy balance
     const int64_t nodes_per_block = (int64_t)block.y * npt;
     dim3 grid((unsigned)((plan->nnode + nodes_per_block - 1) / nodes_per_block),
               (unsigned)((lanes + block.x - 1) / block.x), 1);

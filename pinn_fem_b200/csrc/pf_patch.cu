@@ -81,29 +81,33 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 // Persistent over the problem chunks of one patch, two pipeline stages:
 // while the CTA gathers chunk c out of stage c&1, the row pieces of chunk c+1
-// stream into the other stage.  Index data is staged once per patch and every
-// thread keeps the global row pointers of "its" copies in registers, so the
-// steady state issues ~3 instructions per 512 bytes moved.
-template <int DIM, int MODE, bool BULK>
+// stream into the other stage.  Index data is staged once per patch (already
+// scaled to shared-memory offsets) and every thread keeps the global row
+// pointers of "its" copies in registers, so the steady state issues ~3
+// instructions per 512 bytes moved and ~20 per element evaluation.
+//
+// Stage layout (rows of kChunk doubles): [E of the patch's elements][A ...][x of local nodes * DIM]
+template <int DIM, int MODE, bool MATB, bool STRAIN, bool BULK>
 __global__ void __launch_bounds__(kThreads) patch_gather_kernel(PatchArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: stage0 | stage1 | geo | nodes | elems | ptr | inc | fext/free | reduction | mbarriers
-    const int n_mat_cap = a.mat_batched ? 2 * a.max_elems : 0;
-    const size_t stage_rows = (size_t)n_mat_cap + a.x_rows;
+    const int n_mat_cap = MATB ? 2 * a.max_elems : 0;
+    const int stage_rows = n_mat_cap + a.x_rows;
     double* stage0 = reinterpret_cast<double*>(smem_raw);
-    double4* s_geo = reinterpret_cast<double4*>(stage0 + 2 * stage_rows * kChunk);
-    double* s_fext = reinterpret_cast<double*>(s_geo + a.max_inc);   // [kPatchNodes*DIM] load_factor * f_ext (shared loads)
+    double4* s_geo = reinterpret_cast<double4*>(stage0 + 2 * (size_t)stage_rows * kChunk);
+    double* s_fext = reinterpret_cast<double*>(s_geo + a.max_inc);   // [kPatchNodes*2] load_factor * f_ext (shared loads)
     double* s_red = s_fext + kPatchNodes * 2;                        // [2][kWarps][32]
-    int32_t* s_nodes = reinterpret_cast<int32_t*>(s_red + 2 * kWarps * 32);
+    int2* s_inc = reinterpret_cast<int2*>(s_red + 2 * kWarps * 32);  // {E row offset, x row offset} in doubles
+    int32_t* s_nodes = reinterpret_cast<int32_t*>(s_inc + a.max_inc);
     int32_t* s_elems = s_nodes + a.max_local;
     int32_t* s_ptr = s_elems + a.max_elems;
-    int32_t* s_free = s_ptr + kPatchNodes + 1;                       // [kPatchNodes*DIM]
-    PfPatchInc* s_inc = reinterpret_cast<PfPatchInc*>(s_free + kPatchNodes * 2);
-    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_inc + a.max_inc) + 7) & ~uintptr_t(7));
+    int32_t* s_free = s_ptr + kPatchNodes + 1;                       // [kPatchNodes*2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_free + kPatchNodes * 2) + 7) & ~uintptr_t(7));
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const PfPatch pt = a.patches[blockIdx.x];
+    const int n_mat_rows = MATB ? 2 * pt.n_elem : 0;
+    const int n_rows = n_mat_rows + DIM * pt.n_local;
     if (BULK && tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -114,23 +118,23 @@ __global__ void __launch_bounds__(kThreads) patch_gather_kernel(PatchArgs a) {
     __syncthreads();
     const int n_inc = s_ptr[pt.n_owned];
     for (int i = tid; i < n_inc; i += kThreads) {
-        s_inc[i] = a.patch_inc[pt.inc_off + i];
+        const PfPatchInc pi = a.patch_inc[pt.inc_off + i];
+        s_inc[i] = make_int2(MATB ? pi.lelem * kChunk : a.patch_elems[pt.elem_off + pi.lelem],
+                             (n_mat_rows + pi.lnbr * DIM) * kChunk);
         s_geo[i] = a.patch_inc_geo[pt.inc_off + i];
     }
     if (MODE == 0 && (a.r_out || a.half_sq_part)) {
         for (int i = tid; i < pt.n_owned * DIM; i += kThreads) {
             const int64_t dof = (int64_t)s_nodes[i / DIM] * DIM + (i % DIM);
             s_free[i] = a.dof_free[dof];
-            s_fext[i] = a.fext_bmul ? 0.0 : a.load_factor * a.f_ext[dof];
+            s_fext[i] = a.fext_bmul ? 0.0 : __dmul_rn(a.load_factor, a.f_ext[dof]);
         }
     }
 
-    // rows this thread copies: r = tid / kSegs + i * (kThreads / kSegs); 16-byte segment tid % kSegs
+    // rows this thread copies: r = tid / kSegs + i * kRowsPerPass; 16-byte segment tid % kSegs
     constexpr int kSegs = kRowBytes / 16;
     constexpr int kRowsPerPass = kThreads / kSegs;
     constexpr int kMaxPass = 14;
-    const int n_mat_rows = a.mat_batched ? 2 * pt.n_elem : 0;
-    const int n_rows = n_mat_rows + DIM * pt.n_local;
     auto row_src = [&](int r) -> const double* {
         if (r < n_mat_rows) {
             const int q = r < pt.n_elem ? r : r - pt.n_elem;
@@ -139,41 +143,33 @@ __global__ void __launch_bounds__(kThreads) patch_gather_kernel(PatchArgs a) {
         const int q = r - n_mat_rows;
         return a.x + ((int64_t)s_nodes[q / DIM] * DIM + (q % DIM)) * a.ldb;
     };
-    auto row_dst_off = [&](int r) -> uint32_t {  // byte offset inside a stage
-        if (r < n_mat_rows) return (uint32_t)((r < pt.n_elem ? r : a.max_elems + (r - pt.n_elem)) * kRowBytes);
-        return (uint32_t)((n_mat_cap + (r - n_mat_rows)) * kRowBytes);
-    };
     const int seg = tid % kSegs;
     const char* src[kMaxPass];
-    uint32_t dst[kMaxPass];
 #pragma unroll
     for (int i = 0; i < kMaxPass; ++i) {
         const int r = tid / kSegs + i * kRowsPerPass;
-        src[i] = nullptr;
-        dst[i] = 0;
-        if (r < n_rows) {
-            src[i] = reinterpret_cast<const char*>(row_src(r)) + seg * 16;
-            dst[i] = smem_u32(stage0) + row_dst_off(r) + seg * 16;
-        }
+        src[i] = r < n_rows ? reinterpret_cast<const char*>(row_src(r)) + seg * 16 : nullptr;
     }
-    const uint32_t stage_bytes = (uint32_t)(stage_rows * kRowBytes);
+    const uint32_t stage_bytes = (uint32_t)stage_rows * kRowBytes;
+    const uint32_t my_dst = smem_u32(stage0) + (tid / kSegs) * kRowBytes + seg * 16;
     auto issue = [&](int chunk, int stage) {
         const int64_t boff = (int64_t)chunk * kRowBytes;
         if (BULK) {
             if (tid == 0) mbar_expect_tx(&bars[stage], (uint32_t)n_rows * kRowBytes);
             for (int r = tid; r < n_rows; r += kThreads)
-                bulk_g2s(reinterpret_cast<char*>(stage0) + stage * stage_bytes + row_dst_off(r),
+                bulk_g2s(reinterpret_cast<char*>(stage0) + stage * stage_bytes + r * kRowBytes,
                          reinterpret_cast<const char*>(row_src(r)) + boff, kRowBytes, &bars[stage]);
         } else {
 #pragma unroll
             for (int i = 0; i < kMaxPass; ++i)
                 if (src[i])
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst[i] + stage * stage_bytes),
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(my_dst + stage * stage_bytes +
+                                                                                  i * kRowsPerPass * kRowBytes),
                                  "l"(src[i] + boff)
                                  : "memory");
             for (int r = tid / kSegs + kMaxPass * kRowsPerPass; r < n_rows; r += kRowsPerPass)  // oversize patches
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(stage0) + stage * stage_bytes +
-                                                                              row_dst_off(r) + seg * 16),
+                                                                              r * kRowBytes + seg * 16),
                              "l"(reinterpret_cast<const char*>(row_src(r)) + boff + seg * 16)
                              : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -183,6 +179,7 @@ __global__ void __launch_bounds__(kThreads) patch_gather_kernel(PatchArgs a) {
     const int nchunk = (int)(a.B / kChunk);
     const int c_begin = blockIdx.y * a.chunks_per_cta;
     const int c_end = min(nchunk, c_begin + a.chunks_per_cta);
+    const int a_off = pt.n_elem * kChunk;  // A rows follow the E rows
     __syncthreads();  // index staging done (and mbarriers initialised)
     issue(c_begin, 0);
     for (int c = c_begin; c < c_end; ++c) {
@@ -198,20 +195,19 @@ __global__ void __launch_bounds__(kThreads) patch_gather_kernel(PatchArgs a) {
         } else {
             __syncthreads();
         }
-        const double* sE = stage0 + (size_t)stage * stage_rows * kChunk;
-        const double* sA = sE + (size_t)a.max_elems * kChunk;
-        const double* sX = sE + (size_t)n_mat_cap * kChunk;
+        const double* __restrict__ sb = stage0 + (size_t)stage * stage_rows * kChunk + lane;
         const int64_t b = (int64_t)c * kChunk + lane;
         double sq = 0.0, eps_abs = 0.0;
         for (int l = warp; l < pt.n_owned; l += kWarps) {
-            const double xs = sX[(size_t)(l * DIM) * kChunk + lane];
-            const double ys = DIM == 2 ? sX[(size_t)(l * DIM + 1) * kChunk + lane] : 0.0;
+            const int xoff = (n_mat_rows + l * DIM) * kChunk;
+            const double xs = sb[xoff];
+            const double ys = DIM == 2 ? sb[xoff + kChunk] : 0.0;
             const int64_t d0 = (int64_t)s_nodes[l] * DIM;
             double fex = 0.0, fey = 0.0;
             if (MODE == 0 && (a.r_out || a.half_sq_part)) {
                 if (a.fext_bmul) {  // per-problem loads: fetch early, used after the incidence loop
-                    fex = a.load_factor * __ldg(a.f_ext + d0 * a.ldb + b);
-                    if (DIM == 2) fey = a.load_factor * __ldg(a.f_ext + (d0 + 1) * a.ldb + b);
+                    fex = __dmul_rn(a.load_factor, __ldg(a.f_ext + d0 * a.ldb + b));
+                    if (DIM == 2) fey = __dmul_rn(a.load_factor, __ldg(a.f_ext + (d0 + 1) * a.ldb + b));
                 } else {
                     fex = s_fext[l * DIM];
                     if (DIM == 2) fey = s_fext[l * DIM + 1];
@@ -219,29 +215,31 @@ __global__ void __launch_bounds__(kThreads) patch_gather_kernel(PatchArgs a) {
             }
             double fx = 0.0, fy = 0.0;
             const int k1 = s_ptr[l + 1];
+#pragma unroll 2
             for (int k = s_ptr[l]; k < k1; ++k) {
-                const PfPatchInc inc = s_inc[k];
+                const int2 inc = s_inc[k];
                 const double4 geo = s_geo[k];
                 double Ee, Ae;
-                if (a.mat_batched) {
-                    Ee = sE[(size_t)inc.lelem * kChunk + lane];
-                    Ae = sA[(size_t)inc.lelem * kChunk + lane];
+                if (MATB) {
+                    Ee = sb[inc.x];
+                    Ae = sb[inc.x + a_off];
                 } else {
-                    Ee = __ldg(a.E + s_elems[inc.lelem]);
-                    Ae = __ldg(a.A + s_elems[inc.lelem]);
+                    Ee = __ldg(a.E + inc.x);
+                    Ae = __ldg(a.A + inc.x);
                 }
-                const double xo = sX[(size_t)(inc.lnbr * DIM) * kChunk + lane];
-                const double yo = DIM == 2 ? sX[(size_t)(inc.lnbr * DIM + 1) * kChunk + lane] : 0.0;
+                const double xo = sb[inc.y];
+                const double yo = DIM == 2 ? sb[inc.y + kChunk] : 0.0;
                 const double eps = pf_linear_incidence<DIM>(Ee, Ae, geo, xs, ys, xo, yo, fx, fy);
-                if (MODE == 0) eps_abs = fmax(eps_abs, eps);
+                if (STRAIN) eps_abs = fmax(eps_abs, eps);
             }
             if (a.f_out) {
                 a.f_out[d0 * a.ldb + b] = fx;
                 if (DIM == 2) a.f_out[(d0 + 1) * a.ldb + b] = fy;
             }
             if (MODE == 0 && (a.r_out || a.half_sq_part)) {
-                const double rx = s_free[l * DIM] ? fx - fex : 0.0;
-                const double ry = (DIM == 2 && s_free[l * DIM + 1]) ? fy - fey : 0.0;
+                // r = f_int - load_factor * f_ext, product rounded first like the reference (solver.py:267-269)
+                const double rx = s_free[l * DIM] ? __dsub_rn(fx, fex) : 0.0;
+                const double ry = (DIM == 2 && s_free[l * DIM + 1]) ? __dsub_rn(fy, fey) : 0.0;
                 if (a.r_out) {
                     a.r_out[d0 * a.ldb + b] = rx;
                     if (DIM == 2) a.r_out[(d0 + 1) * a.ldb + b] = ry;
@@ -250,19 +248,21 @@ __global__ void __launch_bounds__(kThreads) patch_gather_kernel(PatchArgs a) {
                 sq += ry * ry;
             }
         }
-        if (MODE == 0 && (a.half_sq_part || a.max_strain_bits)) {
+        const bool reduce = MODE == 0 && (a.half_sq_part || (STRAIN && a.max_strain_bits));
+        if (reduce) {
             s_red[warp * 32 + lane] = sq;
             s_red[(kWarps + warp) * 32 + lane] = eps_abs;
         }
         __syncthreads();  // stage may be refilled by the next iteration's issue; reduction inputs visible
-        if (MODE == 0 && (a.half_sq_part || a.max_strain_bits) && warp == 0) {
+        if (reduce && warp == 0) {
             double acc = 0.0, m = 0.0;
             for (int w = 0; w < kWarps; ++w) {
                 acc += s_red[w * 32 + lane];
                 m = fmax(m, s_red[(kWarps + w) * 32 + lane]);
             }
             if (a.half_sq_part) a.half_sq_part[(int64_t)blockIdx.x * a.ldb + b] = acc;
-            if (a.max_strain_bits) atomicMax(a.max_strain_bits + b, (unsigned long long)__double_as_longlong(m));
+            if (STRAIN && a.max_strain_bits)
+                atomicMax(a.max_strain_bits + b, (unsigned long long)__double_as_longlong(m));
         }
     }
 }
@@ -283,7 +283,7 @@ int pf_patch_gather(pf_plan* plan, const PfGatherCall& c, cudaStream_t st, int64
     static const int disabled = getenv("PF_NO_PATCH") ? atoi(getenv("PF_NO_PATCH")) : 0;
     if (disabled || !plan->patch_ok || plan->patches.empty()) return PF_OK;
     const int64_t ncol = (c.B / kChunk) * kChunk;  // full chunks only; the tail goes to the generic kernel
-    if (ncol == 0 || c.ldb % 2 != 0) return PF_OK;
+    if (ncol < 4 * kChunk || c.ldb % 2 != 0) return PF_OK;  // too few chunks to pipeline: generic kernel
     const double* x = c.mode == 0 ? c.u : c.v;
     auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (!aligned16(x) || (c.mat_batched && (!aligned16(c.E) || !aligned16(c.A)))) return PF_OK;
@@ -292,7 +292,7 @@ int pf_patch_gather(pf_plan* plan, const PfGatherCall& c, cudaStream_t st, int64
     const int x_rows = plan->max_patch_local * dim;
     const size_t stage_rows = (size_t)(c.mat_batched ? 2 * plan->max_patch_elems : 0) + x_rows;
     size_t smem = 2 * stage_rows * kRowBytes;
-    smem += (size_t)plan->max_patch_inc * (sizeof(double4) + sizeof(PfPatchInc));
+    smem += (size_t)plan->max_patch_inc * (sizeof(double4) + sizeof(int2));
     smem += (size_t)(kPatchNodes * 2 + 2 * kWarps * 32) * sizeof(double);
     smem += (size_t)(plan->max_patch_local + plan->max_patch_elems + kPatchNodes + 1 + kPatchNodes * 2) * sizeof(int32_t);
     smem += 64;  // mbarriers + alignment slack
@@ -337,26 +337,32 @@ int pf_patch_gather(pf_plan* plan, const PfGatherCall& c, cudaStream_t st, int64
 
     dim3 grid(npatch, (unsigned)((nchunk + a.chunks_per_cta - 1) / a.chunks_per_cta), 1);
     static const int use_bulk = getenv("PF_PATCH_TMA") ? atoi(getenv("PF_PATCH_TMA")) : 0;
-#define PF_PATCH_LAUNCH1(D, M, T)                                                                                  \
+    const bool strain = c.mode == 0 && c.max_strain != nullptr;
+#define PF_PATCH_LAUNCH(D, M, MB, S, T)                                                                            \
     do {                                                                                                           \
-        PF_CUDA_CHECK(cudaFuncSetAttribute(patch_gather_kernel<D, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           (int)smem));                                                            \
-        patch_gather_kernel<D, M, T><<<grid, kThreads, smem, st>>>(a);                                             \
+        PF_CUDA_CHECK(cudaFuncSetAttribute(patch_gather_kernel<D, M, MB, S, T>,                                    \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+        patch_gather_kernel<D, M, MB, S, T><<<grid, kThreads, smem, st>>>(a);                                      \
     } while (0)
-#define PF_PATCH_LAUNCH(D, M)               \
-    do {                                    \
-        if (use_bulk)                       \
-            PF_PATCH_LAUNCH1(D, M, true);   \
-        else                                \
-            PF_PATCH_LAUNCH1(D, M, false);  \
+#define PF_PATCH_SEL_T(D, M, MB, S)                                                    \
+    do {                                                                               \
+        if (use_bulk) PF_PATCH_LAUNCH(D, M, MB, S, true); else PF_PATCH_LAUNCH(D, M, MB, S, false); \
     } while (0)
-    if (dim == 1) {
-        if (c.mode == 0) PF_PATCH_LAUNCH(1, 0); else PF_PATCH_LAUNCH(1, 1);
-    } else {
-        if (c.mode == 0) PF_PATCH_LAUNCH(2, 0); else PF_PATCH_LAUNCH(2, 1);
-    }
+#define PF_PATCH_SEL_MB(D, M, S)                                                       \
+    do {                                                                               \
+        if (c.mat_batched) PF_PATCH_SEL_T(D, M, true, S); else PF_PATCH_SEL_T(D, M, false, S); \
+    } while (0)
+#define PF_PATCH_SEL_M(D)                                                              \
+    do {                                                                               \
+        if (c.mode == 1) PF_PATCH_SEL_MB(D, 1, false);                                 \
+        else if (strain) PF_PATCH_SEL_MB(D, 0, true);                                  \
+        else PF_PATCH_SEL_MB(D, 0, false);                                             \
+    } while (0)
+    if (dim == 1) PF_PATCH_SEL_M(1); else PF_PATCH_SEL_M(2);
+#undef PF_PATCH_SEL_M
+#undef PF_PATCH_SEL_MB
+#undef PF_PATCH_SEL_T
 #undef PF_PATCH_LAUNCH
-#undef PF_PATCH_LAUNCH1
     PF_CUDA_CHECK(cudaGetLastError());
     if (c.half_sq) {
         patch_column_sum_kernel<<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(plan->d_work, npatch, c.ldb, ncol, 0.5,
