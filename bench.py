@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the PINN-FEM hot path on B200.
+
+Metric (BASELINE.json): element assembly+residual evaluations per second.
+Workload (BASELINE.json configs[4], the synthetic C5 case of SURVEY.md 8d):
+2-D lattice truss, 578 x 578 nodes = 999,941 elements, batched independent
+problems sharing the mesh, 512 problems per GPU (4096 over 8 GPUs: weak
+scaling, problems are sharded by batch with no data-path collective).
+One "step" = one residual evaluation r = f_int(u; E, A) - lambda * f_ext of
+every problem of the shard = 512 x 999,941 element evaluations per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N ...            # CPU restatement of the reference (rank 0)
+
+Rank 0 prints ONE JSON line (see README / DESIGN.md for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+NX = 578
+PROBLEMS_PER_GPU = 512
+CPU_SAMPLE_PROBLEMS_PER_THREAD = 8
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(nelem, nnode, B):
+    """per problem 16*nelem (E, A) + 32*nnode (u read, r write); the mesh
+    indices/coordinates (8*nelem + 16*nnode) are counted once per sweep."""
+    return B * (16 * nelem + 32 * nnode) + 8 * nelem + 16 * nnode
+
+
+def cpu_reference_leg(steps, warmup, sample_problems=None):
+    """Times the CPU restatement of the reference's element loop (oracle/pf_oracle.c, OpenMP over
+    problems) on a bounded sample of the same workload: the full 999,941-element mesh, a slice of
+    the batch."""
+    import numpy as np
+
+    from oracle import c_oracle
+    from oracle import pinnfem_oracle as O
+
+    threads = c_oracle.max_threads()
+    nodes, el, fixed = O.lattice_truss(NX)
+    Bs = sample_problems or threads * CPU_SAMPLE_PROBLEMS_PER_THREAD
+    rng = np.random.default_rng(0)
+    u = rng.uniform(-1e-3, 1e-3, (2 * len(nodes), Bs))
+    E = rng.uniform(0.5, 1.5, (len(el), Bs))
+    A = rng.uniform(0.5, 1.5, (len(el), Bs))
+    fx = rng.normal(scale=1e-3, size=2 * len(nodes))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        c_oracle.residual(nodes, el, E, A, u, fx, 1.0, fixed, want_f=False, want_r=True, nthreads=threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    value = Bs * len(el) * len(times) / total
+    # the reference's own interpreter-bound loop, restated line by line (oracle.assemble_system_loop), on a
+    # tiny sample for context: this is what fem/assembly.py actually costs per element in Python
+    nodes_s, el_s, _ = O.lattice_truss(24)
+    t0 = time.perf_counter()
+    O.assemble_system_loop(nodes_s, el_s, 1.0, 1.0, np.zeros(2 * len(nodes_s)))
+    py_rate = len(el_s) / (time.perf_counter() - t0)
+    return {"value": value, "unit": "element_evals/s", "cores": threads, "kind": "port",
+            "sample": f"{Bs} of {PROBLEMS_PER_GPU} problems x full {len(el)}-element mesh per step, "
+                      f"{len(times)} steps, C restatement with OpenMP over problems",
+            "python_loop_element_evals_per_s": py_rate, "ms_per_step": 1e3 * total / len(times)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--problems-per-gpu", type=int, default=PROBLEMS_PER_GPU)
+    ap.add_argument("--nx", type=int, default=NX)
+    ap.add_argument("--e2e-problems", type=int, default=0, help="problems in the host-buffer leg (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gd", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    nelem_full = 2 * (args.nx - 1) * args.nx + (args.nx - 1) ** 2
+    config = {"workload": f"synthetic 2D lattice truss {args.nx}x{args.nx} nodes, {nelem_full} elements x "
+                          f"{args.problems_per_gpu} batched problems per GPU "
+                          f"({args.problems_per_gpu * max(world, args.gpus)} total), linear bar element, "
+                          f"E and A per (element, problem), residual r = f_int - lambda*f_ext",
+              "sharding": "batch (independent problems), no data-path collective",
+              "cache": "inputs per step (13.7 GB) are far larger than the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 5))
+        base = cpu_reference_leg(steps, min(args.warmup, 1))
+        line = {"impl": "reference", "metric": "element assembly+residual evals/sec", "value": base["value"],
+                "unit": "element_evals/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+                "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": base["value"], "unit": "element_evals/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "reference is pure Python (no compiled code to build); this arm times the C/OpenMP "
+                        "restatement of its element loop on all host threads. The literal Python loop runs at "
+                        f"{base['python_loop_element_evals_per_s']:.0f} element_evals/s on one core."}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pinn_fem_b200 import AssemblyPlan
+    from pinn_fem_b200.meshes import lattice_truss
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: pinn_fem_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    nodes, el, fixed = lattice_truss(args.nx)
+    plan = AssemblyPlan(nodes, el, fixed, device=dev)
+    B = args.problems_per_gpu
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    u = (torch.rand((plan.ndof, B), generator=g, device=dev, dtype=torch.float64) - 0.5) * 2e-3
+    E = torch.rand((plan.nelem, B), generator=g, device=dev, dtype=torch.float64) + 0.5
+    A = torch.rand((plan.nelem, B), generator=g, device=dev, dtype=torch.float64) + 0.5
+    fx = torch.randn(plan.ndof, generator=g, device=dev, dtype=torch.float64) * 1e-3
+    r = torch.empty_like(u)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        plan.residual_into(u, E, A, fx, 1.0, r)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        plan.residual_into(u, E, A, fx, 1.0, r)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    ms_t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * B * plan.nelem * args.steps / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant (only) kernel of the step: one patch_gather launch per step -------------
+    peak, peak_src = measured_peaks()
+    ab = algorithmic_bytes(plan.nelem, plan.nnode, B)
+    kernel_ms = ms / args.steps  # this rank's average launch duration (launches are back to back on one stream)
+    achieved = ab / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "r1_traffic.json"
+    if tp.exists():
+        with open(tp) as f:
+            t = json.load(f)
+        if t.get("nx") == args.nx and t.get("problems") == B:
+            traffic = t.get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "patch_gather_kernel<2,0,true,false,false>", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ab, "kernel_ms": kernel_ms}
+
+    # ---- end to end through the public host-buffer API (pinned host -> device -> pinned host) --------------
+    Be = args.e2e_problems
+    if Be <= 0:
+        try:
+            with open("/proc/meminfo") as f:
+                avail_kb = next(int(l.split()[1]) for l in f if l.startswith("MemAvailable"))
+        except Exception:
+            avail_kb = 0
+        full_bytes = (2 * plan.ndof + 2 * plan.nelem) * B * 8
+        Be = B if avail_kb * 1024 > 4 * full_bytes * max(world, 1) else min(B, 128)
+    uh = torch.empty((plan.ndof, Be), dtype=torch.float64, pin_memory=True)
+    Eh = torch.empty((plan.nelem, Be), dtype=torch.float64, pin_memory=True)
+    Ah = torch.empty((plan.nelem, Be), dtype=torch.float64, pin_memory=True)
+    rh = torch.empty((plan.ndof, Be), dtype=torch.float64, pin_memory=True)
+    uh.copy_(u[:, :Be])
+    Eh.copy_(E[:, :Be])
+    Ah.copy_(A[:, :Be])
+    fxh = fx.cpu()
+    torch.cuda.synchronize(dev)
+    e2e_steps = max(1, min(args.steps, 3))
+    plan.residual_host(uh, Eh, Ah, fxh, 1.0, rh)  # warm-up: allocates the staging buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.residual_host(uh, Eh, Ah, fxh, 1.0, rh)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * Be * plan.nelem * e2e_steps / float(e2e_t.item())
+    e2e_ok = bool(torch.equal(rh[:, :8], r[:, :8].cpu()))
+    e2e = {"value": e2e_value, "unit": "element_evals/s",
+           "h2d_bytes_per_step": (plan.ndof + 2 * plan.nelem) * Be * 8 + plan.ndof * 8,
+           "d2h_bytes_per_step": plan.ndof * Be * 8, "problems_per_gpu": Be, "steps": e2e_steps,
+           "api": "AssemblyPlan.residual_host -> pf_residual_host (pinned host buffers, chunked H2D/compute/D2H "
+                  "pipeline on 3 streams)", "matches_device_result": e2e_ok}
+    launches = args.steps + e2e_steps * ((Be + 127) // 128)
+
+    extra = {}
+    if not args.no_gd:
+        try:
+            from pinn_fem_b200.bench_gd import gd_iterations_per_second
+
+            extra["pinn_gd"] = gd_iterations_per_second(dev, world)
+            launches += extra["pinn_gd"].get("gpu_launches", 0)
+        except Exception as exc:  # the headline metric must not depend on the secondary one
+            extra["pinn_gd"] = {"error": f"{type(exc).__name__}: {exc}"}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        b = cpu_reference_leg(2, 1)
+        cpu_base = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_base["python_loop_element_evals_per_s"] = b["python_loop_element_evals_per_s"]
+
+    if rank == 0:
+        line = {"metric": "element assembly+residual evals/sec", "value": value, "unit": "element_evals/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (torch.Generator seed 1234+rank: u~U(-1e-3,1e-3), E,A~U(0.5,1.5), lambda=1)",
+                "config": config, "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e,
+                "gpu_launches": launches, "clocks": clocks}
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

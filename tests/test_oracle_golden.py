@@ -354,3 +354,28 @@ def test_lattice_generator_counts():
     # C5 sizes from the closed form, without building the mesh
     nx = 578
     assert nx * nx == 334084 and 2 * (nx - 1) * nx + (nx - 1) ** 2 == 999941
+
+
+def test_c_oracle_matches_numpy_oracle(assembly_golden):
+    """oracle/pf_oracle.c (the multi-threaded CPU baseline) against the golden
+    vectors and the NumPy restatement."""
+    from oracle import c_oracle
+
+    for name in ("fem2d_like", "lattice5x3_perturbed", "bar1d"):
+        c = _case(assembly_golden, name)
+        f, _ = c_oracle.residual(c["nodes"], c["elements"], c["E"], c["A"], c["u"])
+        assert rel(f, c["f_int"]) < 1e-13
+    c = _case(assembly_golden, "lattice8")
+    rng = np.random.default_rng(3)
+    B = 19
+    u = rng.uniform(-1e-3, 1e-3, size=(len(c["u"]), B))
+    E = rng.uniform(0.5, 1.5, size=(len(c["E"]), B))
+    A = rng.uniform(0.5, 1.5, size=(len(c["E"]), B))
+    fx = rng.normal(size=len(c["u"]))
+    for kind in (O.LINEAR, O.GREEN_LAGRANGE):
+        f, r = c_oracle.residual(c["nodes"], c["elements"], E, A, u, fx, 0.3, c["fixed_in"], kind, want_r=True)
+        f_ref, _ = O.assemble_residual(c["nodes"], c["elements"], E, A, u, 2, kind)
+        assert rel(f, f_ref) < 1e-13
+        r_ref = np.zeros_like(f_ref)
+        r_ref[c["free"]] = f_ref[c["free"]] - 0.3 * fx[c["free"]][:, None]
+        assert rel(r, r_ref) < 1e-13
