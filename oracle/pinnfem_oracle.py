@@ -643,7 +643,7 @@ class Adam:
         bc2 = 1.0 - b2**self.t
         step_size = self.lr / bc1
         denom = np.sqrt(self.v) / math.sqrt(bc2) + eps
-        p -= step_size * (self.m / denom)
+        p += (-step_size * self.m) / denom  # addcdiv_(exp_avg, denom, value=-step_size)
 
 
 def gd_loss_and_grads(mesh: Mesh, mat: MaterialNets, u, lam, meas_dofs, meas_vals, alpha_p, alpha_d,

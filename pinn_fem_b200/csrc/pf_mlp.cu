@@ -12,8 +12,8 @@
 
 namespace {
 
-constexpr int PTS = 128;        // points per CTA
-constexpr int PS = PTS + 1;     // padded row stride of the activation tiles
+// PTS = points per CTA (128, 64 or 32: the largest whose tiles fit in shared memory);
+// activation tiles use a padded row stride PTS + 1.
 
 // shared-memory plan of one CTA (in doubles)
 struct SmemPlan {
@@ -26,7 +26,8 @@ struct SmemPlan {
     int total;
 };
 
-__host__ __device__ inline SmemPlan smem_plan(const PfMlpDesc& d, bool backward) {
+__host__ __device__ inline SmemPlan smem_plan(const PfMlpDesc& d, bool backward, int PTS) {
+    const int PS = PTS + 1;
     SmemPlan s;
     int off = 0;
     for (int l = 0; l < d.L; ++l) {
@@ -69,6 +70,7 @@ __device__ void stage_weights(const PfMlpDesc& d, const SmemPlan& s, const doubl
 }
 
 // One hidden layer for the calling thread's point: out[o][t] = tanh(b[o] + sum_i Wt[i][o] in[i][t]).
+template <int PS>
 __device__ __forceinline__ void hidden_layer(const double* __restrict__ Wt, const double* __restrict__ b, int in,
                                              int wp, const double* __restrict__ a_in, double* __restrict__ a_out,
                                              int t) {
@@ -90,6 +92,7 @@ __device__ __forceinline__ void hidden_layer(const double* __restrict__ Wt, cons
     }
 }
 
+template <int PS>
 __device__ __forceinline__ void load_input(const PfMlpDesc& d, const double* __restrict__ X,
                                            const double* __restrict__ centroid, double load_factor, int64_t p,
                                            int64_t n, double* __restrict__ a0, int t) {
@@ -101,22 +104,24 @@ __device__ __forceinline__ void load_input(const PfMlpDesc& d, const double* __r
     }
 }
 
+template <int PTS>
 __global__ void __launch_bounds__(PTS) mlp_forward_kernel(PfMlpDesc d, const double* __restrict__ theta, int64_t n,
                                                           const double* __restrict__ X,
                                                           const double* __restrict__ centroid, double load_factor,
                                                           double scale, int positive, double* __restrict__ out) {
+    constexpr int PS = PTS + 1;
     extern __shared__ __align__(16) double sm[];
-    const SmemPlan s = smem_plan(d, false);
+    const SmemPlan s = smem_plan(d, false, PTS);
     stage_weights(d, s, theta, sm);
     const int t = threadIdx.x;
     const int64_t p = (int64_t)blockIdx.x * PTS + t;
     const int maxrow = d.wp > d.in_dim ? d.wp : d.in_dim;
     double* buf0 = sm + s.act_off;
     double* buf1 = buf0 + maxrow * PS;
-    load_input(d, X, centroid, load_factor, p, n, buf0, t);
+    load_input<PS>(d, X, centroid, load_factor, p, n, buf0, t);
     __syncthreads();
     for (int l = 0; l < d.L; ++l) {
-        hidden_layer(sm + s.w_off[l], sm + s.b_off[l], l == 0 ? d.in_dim : d.w, d.wp, buf0, buf1, t);
+        hidden_layer<PS>(sm + s.w_off[l], sm + s.b_off[l], l == 0 ? d.in_dim : d.w, d.wp, buf0, buf1, t);
         double* tmp = buf0;
         buf0 = buf1;
         buf1 = tmp;
@@ -128,15 +133,16 @@ __global__ void __launch_bounds__(PTS) mlp_forward_kernel(PfMlpDesc d, const dou
 
 // mode 0: reduce parameter gradients over the CTA's points -> gpart[blockIdx.x][n_params]
 // mode 1: per-point Jacobian rows                            -> jac[p][n_params]
-template <int MODE>
+template <int MODE, int PTS>
 __global__ void __launch_bounds__(PTS) mlp_backward_kernel(PfMlpDesc d, const double* __restrict__ theta, int64_t n,
                                                            const double* __restrict__ X,
                                                            const double* __restrict__ centroid, double load_factor,
                                                            double scale, int positive,
                                                            const double* __restrict__ g_out,
                                                            double* __restrict__ dst) {
+    constexpr int PS = PTS + 1;
     extern __shared__ __align__(16) double sm[];
-    const SmemPlan s = smem_plan(d, true);
+    const SmemPlan s = smem_plan(d, true, PTS);
     stage_weights(d, s, theta, sm);
     const int t = threadIdx.x;
     const int64_t p0 = (int64_t)blockIdx.x * PTS;
@@ -144,10 +150,10 @@ __global__ void __launch_bounds__(PTS) mlp_backward_kernel(PfMlpDesc d, const do
     const int npts = (int)((n - p0) < PTS ? (n - p0) : PTS);
     double* acts = sm + s.act_off;  // layer 0 rows: in_dim; layer l>=1 rows: wp each
     auto act = [&](int l) { return acts + (l == 0 ? 0 : (d.in_dim + (l - 1) * d.wp)) * PS; };
-    load_input(d, X, centroid, load_factor, p, n, act(0), t);
+    load_input<PS>(d, X, centroid, load_factor, p, n, act(0), t);
     __syncthreads();
     for (int l = 0; l < d.L; ++l)
-        hidden_layer(sm + s.w_off[l], sm + s.b_off[l], l == 0 ? d.in_dim : d.w, d.wp, act(l), act(l + 1), t);
+        hidden_layer<PS>(sm + s.w_off[l], sm + s.b_off[l], l == 0 ? d.in_dim : d.w, d.wp, act(l), act(l + 1), t);
     double z = sm[s.bo_off];
     for (int i = 0; i < d.w; ++i) z = fma(sm[s.wo_off + i], act(d.L)[i * PS + t], z);
     double dz = 0.0;
@@ -296,12 +302,37 @@ static int mlp_common(pf_plan* plan, int input_dim, int hidden_layers, int width
     return PF_OK;
 }
 
+constexpr size_t kSmemLimit = 220 * 1024;
+
+static int pick_pts(const PfMlpDesc& d, bool backward, int* pts, size_t* smem) {
+    for (int cand : {128, 64, 32}) {
+        const size_t bytes = (size_t)smem_plan(d, backward, cand).total * sizeof(double);
+        if (bytes <= kSmemLimit) {
+            *pts = cand;
+            *smem = bytes;
+            return PF_OK;
+        }
+    }
+    pf_set_error("network too large for the shared-memory MLP kernels");
+    return PF_ERR_ARG;
+}
+
 template <typename Kernel>
 static int set_smem(Kernel k, size_t bytes) {
-    PF_REQUIRE(bytes <= 220 * 1024, "network too large for the shared-memory MLP kernels (%zu bytes)", bytes);
     if (bytes > 48 * 1024) PF_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return PF_OK;
 }
+
+#define PF_MLP_DISPATCH(PTSV, CALL) \
+    do {                            \
+        if ((PTSV) == 128) {        \
+            CALL(128);              \
+        } else if ((PTSV) == 64) {  \
+            CALL(64);               \
+        } else {                    \
+            CALL(32);               \
+        }                           \
+    } while (0)
 
 extern "C" int pf_mlp_forward(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta,
                               int64_t n, const double* X, double load_factor, double scale, int enforce_positive,
@@ -312,10 +343,18 @@ extern "C" int pf_mlp_forward(pf_plan* plan, int input_dim, int hidden_layers, i
     if (rc) return rc;
     PF_REQUIRE(out != nullptr, "out is NULL");
     if (n == 0) return PF_OK;
-    const size_t smem = (size_t)smem_plan(d, false).total * sizeof(double);
-    if ((rc = set_smem(mlp_forward_kernel, smem))) return rc;
-    mlp_forward_kernel<<<(unsigned)((n + PTS - 1) / PTS), PTS, smem, pf_stream_of(stream)>>>(
-        d, theta, n, X, cen, load_factor, scale, enforce_positive, out);
+    int pts;
+    size_t smem;
+    if ((rc = pick_pts(d, false, &pts, &smem))) return rc;
+    cudaStream_t st = pf_stream_of(stream);
+#define PF_FWD(P)                                                                                             \
+    do {                                                                                                      \
+        if ((rc = set_smem(mlp_forward_kernel<P>, smem))) return rc;                                          \
+        mlp_forward_kernel<P><<<(unsigned)((n + P - 1) / P), P, smem, st>>>(d, theta, n, X, cen, load_factor, \
+                                                                           scale, enforce_positive, out);     \
+    } while (0)
+    PF_MLP_DISPATCH(pts, PF_FWD);
+#undef PF_FWD
     PF_CUDA_CHECK(cudaGetLastError());
     return PF_OK;
 }
@@ -354,13 +393,20 @@ extern "C" int pf_mlp_backward(pf_plan* plan, int input_dim, int hidden_layers, 
         PF_CUDA_CHECK(cudaMemsetAsync(g_theta, 0, d.n_params * sizeof(double), st));
         return PF_OK;
     }
-    const size_t smem = (size_t)smem_plan(d, true).total * sizeof(double);
-    if ((rc = set_smem(mlp_backward_kernel<0>, smem))) return rc;
-    const unsigned blocks = (unsigned)((n + PTS - 1) / PTS);
+    int pts;
+    size_t smem;
+    if ((rc = pick_pts(d, true, &pts, &smem))) return rc;
+    const unsigned blocks = (unsigned)((n + pts - 1) / pts);
     double* part = g_theta;
     if (blocks > 1 && (rc = scratch(plan, (size_t)blocks * d.n_params * sizeof(double), &part))) return rc;
-    mlp_backward_kernel<0><<<blocks, PTS, smem, st>>>(d, theta, n, X, cen, load_factor, scale, enforce_positive,
-                                                      g_out, part);
+#define PF_BWD(P)                                                                                               \
+    do {                                                                                                        \
+        if ((rc = set_smem(mlp_backward_kernel<0, P>, smem))) return rc;                                        \
+        mlp_backward_kernel<0, P><<<blocks, P, smem, st>>>(d, theta, n, X, cen, load_factor, scale,             \
+                                                           enforce_positive, g_out, part);                      \
+    } while (0)
+    PF_MLP_DISPATCH(pts, PF_BWD);
+#undef PF_BWD
     PF_CUDA_CHECK(cudaGetLastError());
     if (blocks > 1) {
         reduce_rows_kernel<<<(d.n_params + 127) / 128, 128, 0, st>>>(part, blocks, d.n_params, g_theta);
@@ -378,10 +424,19 @@ extern "C" int pf_mlp_param_jacobian(pf_plan* plan, int input_dim, int hidden_la
     if (rc) return rc;
     PF_REQUIRE(jac != nullptr, "jac is NULL");
     if (n == 0) return PF_OK;
-    const size_t smem = (size_t)smem_plan(d, true).total * sizeof(double);
-    if ((rc = set_smem(mlp_backward_kernel<1>, smem))) return rc;
-    mlp_backward_kernel<1><<<(unsigned)((n + PTS - 1) / PTS), PTS, smem, pf_stream_of(stream)>>>(
-        d, theta, n, X, cen, load_factor, scale, enforce_positive, nullptr, jac);
+    int pts;
+    size_t smem;
+    if ((rc = pick_pts(d, true, &pts, &smem))) return rc;
+    cudaStream_t st = pf_stream_of(stream);
+#define PF_JAC(P)                                                                                              \
+    do {                                                                                                       \
+        if ((rc = set_smem(mlp_backward_kernel<1, P>, smem))) return rc;                                       \
+        mlp_backward_kernel<1, P><<<(unsigned)((n + P - 1) / P), P, smem, st>>>(d, theta, n, X, cen,          \
+                                                                                load_factor, scale,            \
+                                                                                enforce_positive, nullptr, jac); \
+    } while (0)
+    PF_MLP_DISPATCH(pts, PF_JAC);
+#undef PF_JAC
     PF_CUDA_CHECK(cudaGetLastError());
     return PF_OK;
 }

@@ -6,8 +6,6 @@
     pf_set_error(name ": not implemented yet");     \
     return PF_ERR_ARG
 
-extern "C" int pf_gd_solve(pf_plan*, const pf_gd_config*, int64_t, double*, double*, const double*, const int32_t*,
-                           const double*, double*, int32_t*, int32_t*, double*, void*) { PF_TODO("pf_gd_solve"); }
 extern "C" int pf_solve_dense(int64_t, int64_t, double*, double*, int32_t*, void*) { PF_TODO("pf_solve_dense"); }
 extern "C" int pf_cg_solve(pf_plan*, int, int64_t, const double*, const double*, const double*, int, const double*,
                            double*, double, int, double*, int64_t, int32_t*, double*, void*) { PF_TODO("pf_cg_solve"); }

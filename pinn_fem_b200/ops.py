@@ -1,0 +1,168 @@
+"""Thin torch-facing wrappers over the C-ABI entry points that are not tied to
+an :class:`AssemblyPlan` method: material networks, the device-resident
+gradient-descent loop, dense solves and the Gauss-Newton normal equations.
+All tensors are float64 CUDA tensors; nothing here computes on the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check
+from .plan import AssemblyPlan, _ptr, _stream_ptr
+
+
+@dataclass(frozen=True)
+class NetSpec:
+    """SimpleNN architecture (examples/json/generic.py:118-142)."""
+
+    input_dim: int
+    hidden_layers: int
+    width: int
+
+    @property
+    def n_params(self) -> int:
+        n = int(_lib.load().pf_mlp_num_params(self.input_dim, self.hidden_layers, self.width))
+        if n < 0:
+            raise ValueError(f"unsupported network {self}")
+        return n
+
+
+def _dev_f64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise ValueError(f"{name} must be a contiguous float64 CUDA tensor")
+    return t
+
+
+def _mlp_args(spec: NetSpec, theta, X, plan):
+    theta = _dev_f64(theta, "theta")
+    if theta.numel() != spec.n_params:
+        raise ValueError(f"theta has {theta.numel()} entries, network needs {spec.n_params}")
+    if X is None:
+        if plan is None:
+            raise ValueError("either X or a plan (element centroids) is required")
+        return theta, None, plan.nelem, plan._handle, plan.device
+    X = _dev_f64(X, "X")
+    if X.dim() != 2 or X.shape[1] != spec.input_dim:
+        raise ValueError(f"X must be [n, {spec.input_dim}]")
+    return theta, X, X.shape[0], (plan._handle if plan is not None else None), X.device
+
+
+def mlp_forward(spec: NetSpec, theta, X=None, plan: Optional[AssemblyPlan] = None, load_factor=1.0, scale=1.0,
+                enforce_positive=True) -> torch.Tensor:
+    """``softplus(net(x)) * scale`` (fem/properties.py:150-156) at the rows of X, or at
+    the plan's element centroids with inputs ``[load_factor, x_c(, y_c)]``."""
+    theta, X, n, handle, dev = _mlp_args(spec, theta, X, plan)
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().pf_mlp_forward(handle, spec.input_dim, spec.hidden_layers, spec.width, _ptr(theta), n,
+                                         _ptr(X), float(load_factor), float(scale), int(enforce_positive),
+                                         _ptr(out), _stream_ptr(dev)))
+    return out
+
+
+def mlp_backward(spec: NetSpec, theta, g_out, X=None, plan=None, load_factor=1.0, scale=1.0,
+                 enforce_positive=True) -> torch.Tensor:
+    """dL/dtheta (flat) given dL/dvalue per point."""
+    theta, X, n, handle, dev = _mlp_args(spec, theta, X, plan)
+    g_out = _dev_f64(g_out, "g_out")
+    if g_out.numel() != n:
+        raise ValueError("g_out must have one entry per point")
+    g_theta = torch.empty(spec.n_params, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().pf_mlp_backward(handle, spec.input_dim, spec.hidden_layers, spec.width, _ptr(theta), n,
+                                          _ptr(X), float(load_factor), float(scale), int(enforce_positive),
+                                          _ptr(g_out), _ptr(g_theta), _stream_ptr(dev)))
+    return g_theta
+
+
+def mlp_param_jacobian(spec: NetSpec, theta, X=None, plan=None, load_factor=1.0, scale=1.0,
+                       enforce_positive=True) -> torch.Tensor:
+    """``jac[p, :] = d value_p / d theta`` for every point."""
+    theta, X, n, handle, dev = _mlp_args(spec, theta, X, plan)
+    jac = torch.empty((n, spec.n_params), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().pf_mlp_param_jacobian(handle, spec.input_dim, spec.hidden_layers, spec.width, _ptr(theta),
+                                                n, _ptr(X), float(load_factor), float(scale),
+                                                int(enforce_positive), _ptr(jac), _stream_ptr(dev)))
+    return jac
+
+
+@dataclass
+class GDResult:
+    u: torch.Tensor            # [nprob, ndof]
+    theta: torch.Tensor        # [nprob, n_theta]
+    reactions: torch.Tensor    # [nprob, ndof]
+    history: torch.Tensor      # [nprob, max_iterations, 7] (rows beyond n_iters are undefined)
+    n_iters: torch.Tensor      # int32 [nprob]
+    converged: torch.Tensor    # int32 [nprob]
+
+
+def gd_solve(plan: AssemblyPlan, nets: Sequence[Optional[NetSpec]], scales: Sequence[float], theta, u, f_ext,
+             meas_dofs=None, meas_vals=None, *, max_iterations=1000, tolerance=1e-6, learning_rate_u=1e-7,
+             learning_rate_theta=1e-4, alpha_physics=1.0, alpha_data=100.0, load_factor=1.0,
+             record_history=True) -> GDResult:
+    """Run ``solve_gd``'s inner loop (fem/solver.py:252-355) on the device for ``nprob``
+    independent problems sharing ``plan``.  ``nets[k]`` is the architecture of
+    property k (young, area, density) or None for a scalar of value ``scales[k]``;
+    ``theta`` is ``[nprob, sum(n_params of enabled nets)]`` and is updated in place,
+    as is ``u`` ``[nprob, ndof]``."""
+    plan._need_device()
+    dev = plan.device
+    u = _dev_f64(u, "u")
+    if u.dim() == 1:
+        u = u.unsqueeze(0)
+    nprob = u.shape[0]
+    if u.shape[1] != plan.ndof:
+        raise ValueError(f"u must be [nprob, {plan.ndof}]")
+    cfg = _lib.GDConfig()
+    cfg.max_iterations = int(max_iterations)
+    cfg.kind = _lib.ELEM_LINEAR
+    cfg.tolerance = float(tolerance)
+    cfg.learning_rate_u = float(learning_rate_u)
+    cfg.learning_rate_theta = float(learning_rate_theta)
+    cfg.alpha_physics = float(alpha_physics)
+    cfg.alpha_data = float(alpha_data)
+    cfg.load_factor = float(load_factor)
+    ntheta = 0
+    for k in range(3):
+        spec = nets[k] if k < len(nets) else None
+        cfg.net_enabled[k] = 1 if spec is not None else 0
+        cfg.net_scale[k] = float(scales[k]) if k < len(scales) else 0.0
+        if spec is not None:
+            cfg.net_input_dim[k], cfg.net_hidden_layers[k], cfg.net_width[k] = spec.input_dim, spec.hidden_layers, spec.width
+            ntheta += spec.n_params
+    if ntheta:
+        theta = _dev_f64(theta, "theta")
+        if theta.dim() == 1:
+            theta = theta.unsqueeze(0)
+        if tuple(theta.shape) != (nprob, ntheta):
+            raise ValueError(f"theta must be [{nprob}, {ntheta}], got {tuple(theta.shape)}")
+    else:
+        theta = torch.empty((nprob, 0), dtype=torch.float64, device=dev)
+    f_ext = _dev_f64(f_ext, "f_ext")
+    n_meas = 0
+    md = mv = None
+    if meas_dofs is not None and meas_vals is not None and len(meas_dofs) > 0:
+        md = torch.as_tensor(meas_dofs, device=dev).to(torch.int32).contiguous()
+        mv = torch.as_tensor(meas_vals, dtype=torch.float64, device=dev)
+        if mv.dim() == 1:
+            mv = mv.unsqueeze(0).expand(nprob, -1)
+        mv = mv.contiguous()
+        n_meas = md.numel()
+        if tuple(mv.shape) != (nprob, n_meas):
+            raise ValueError("meas_vals must be [n_measured] or [nprob, n_measured]")
+    cfg.n_measured = n_meas
+    history = (torch.empty((nprob, max(int(max_iterations), 1), _lib.GD_HISTORY_COLS), dtype=torch.float64, device=dev)
+               if record_history else None)
+    n_iters = torch.zeros(nprob, dtype=torch.int32, device=dev)
+    converged = torch.zeros(nprob, dtype=torch.int32, device=dev)
+    reactions = torch.empty((nprob, plan.ndof), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().pf_gd_solve(plan._handle, C.byref(cfg), nprob, _ptr(theta) if ntheta else None, _ptr(u),
+                                      _ptr(f_ext), _ptr(md), _ptr(mv), _ptr(history), _ptr(n_iters), _ptr(converged),
+                                      _ptr(reactions), _stream_ptr(dev)))
+    return GDResult(u=u, theta=theta, reactions=reactions, history=history, n_iters=n_iters, converged=converged)
