@@ -238,6 +238,19 @@ int64_t pf_cg_work_len(const pf_plan* plan, int64_t B);
 int pf_gn_normal_equations(int64_t m, int64_t n, const double* J, const double* R, double damping_factor,
                            double* jtj, double* jtr, double* damping_out, void* stream);
 
+/* Stacked Gauss-Newton Jacobian (fem/nn_solver.py:50-135, :223-239), dense row-major
+ *   J dev [(nfree + n_meas)][nfree + nE + nA + n_rest]:
+ *     rows 0..nfree-1     [ alpha_physics*K_ff | alpha_physics*d f_int[free]/d theta ]
+ *     rows nfree..        [ alpha_data*(-1 at the measured free DOF) | 0 ]
+ *   vals    dev BSR tangent values from pf_tangent_bsr (B = 1)
+ *   jacE    dev [nelem][nE] = d E_e / d theta_E from pf_mlp_param_jacobian (NULL when nE == 0), jacA alike
+ *   n_rest  trailing all-zero parameter columns (density: it never enters the physics)
+ * replaces the n_free x n_tensors reverse passes of compute_jacobian_blocks. */
+int pf_gn_jacobian(pf_plan* plan, int kind, const double* u, const double* E, const double* A, const double* vals,
+                   const double* jacE, int64_t nE, const double* jacA, int64_t nA, int64_t n_rest,
+                   double alpha_physics, double alpha_data, const int32_t* meas_dofs, int64_t n_meas, double* J,
+                   void* stream);
+
 /* ------------------------------------------------------------------------
  * Host-buffer convenience entry point (the end-to-end path): residual of B
  * problems whose u/E/A live in (pinned) host memory, streamed through the

@@ -1,0 +1,498 @@
+// Linear solves (fp64).
+//
+//  * pf_solve_dense: LU with partial pivoting, the algorithm behind
+//    np.linalg.solve (fem/core.py:35, fem/solver.py:464) and torch.linalg.solve
+//    (fem/nn_solver.py:277).
+//      - n <= 120: one CTA per system, the augmented matrix [A | b] lives in
+//        shared memory (batched Newton steps on small meshes);
+//      - larger n: blocked right-looking LU in global memory (L2 resident up to
+//        n ~ 3000): single-CTA panel factorisation with warp-shuffle pivot
+//        search, then row swaps + triangular solve and a tiled rank-32 update
+//        spread over all SMs.  Used by the Gauss-Newton/LM step.
+//  * pf_cg_solve: Jacobi-preconditioned conjugate gradients on the free DOFs,
+//    matrix-free through the assembly mat-vec kernel, batched over problems,
+//    with fixed-order (deterministic) two-stage dot products.
+#include <algorithm>
+#include <cmath>
+
+#include "pf_internal.h"
+
+namespace {
+
+constexpr int kSmallMax = 120;
+
+// argmax |x| with the lowest index winning ties (LAPACK idamax semantics)
+__device__ __forceinline__ void warp_argmax(double& v, int& i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+        if (v2 > v || (v2 == v && i2 < i)) {
+            v = v2;
+            i = i2;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) lu_small_kernel(int n, double* __restrict__ Ag, double* __restrict__ bg,
+                                                       int32_t* __restrict__ info) {
+    extern __shared__ double s[];
+    const int ld = n + 1 + (n & 1);  // n+1 columns (b is the last), odd row stride: conflict-free column walks
+    double* A = s;                   // [n][ld], column n holds b
+    __shared__ int s_piv;
+    __shared__ int s_info;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* Asrc = Ag + (size_t)blockIdx.x * n * n;
+    double* bsrc = bg + (size_t)blockIdx.x * n;
+    for (int q = tid; q < n * n; q += nt) A[(q / n) * ld + (q % n)] = Asrc[q];
+    for (int q = tid; q < n; q += nt) A[q * ld + n] = bsrc[q];
+    if (tid == 0) s_info = 0;
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        if (tid < 32) {
+            double best = -1.0;
+            int bi = k;
+            for (int i = k + tid; i < n; i += 32) {
+                const double v = fabs(A[i * ld + k]);
+                if (v > best) {
+                    best = v;
+                    bi = i;
+                }
+            }
+            warp_argmax(best, bi);
+            if (tid == 0) {
+                s_piv = bi;
+                if (best == 0.0 && s_info == 0) s_info = k + 1;
+            }
+        }
+        __syncthreads();
+        const int p = s_piv;
+        if (p != k)
+            for (int c = tid; c <= n; c += nt) {
+                const double t = A[k * ld + c];
+                A[k * ld + c] = A[p * ld + c];
+                A[p * ld + c] = t;
+            }
+        __syncthreads();
+        const double piv = A[k * ld + k];
+        if (piv != 0.0) {
+            const int rows = n - k - 1, cols = n - k;  // columns k+1..n (incl. rhs)
+            for (int q = tid; q < rows * cols; q += nt) {
+                const int i = k + 1 + q / cols, c = k + 1 + q % cols;
+                const double l = A[i * ld + k] / piv;
+                A[i * ld + c] = fma(-l, A[k * ld + c], A[i * ld + c]);
+            }
+        }
+        __syncthreads();
+    }
+    // back substitution (column oriented: one barrier per unknown)
+    for (int i = n - 1; i >= 0; --i) {
+        const double d = A[i * ld + i];
+        if (tid == 0) A[i * ld + n] = d != 0.0 ? A[i * ld + n] / d : A[i * ld + n];
+        __syncthreads();
+        const double xi = A[i * ld + n];
+        for (int r = tid; r < i; r += nt) A[r * ld + n] = fma(-A[r * ld + i], xi, A[r * ld + n]);
+        __syncthreads();
+    }
+    for (int q = tid; q < n; q += nt) bsrc[q] = A[q * ld + n];
+    if (tid == 0) info[blockIdx.x] = s_info;
+}
+
+// ---- blocked LU for one large system -------------------------------------------------
+constexpr int NB = 32;
+
+// Factor the panel A[k0:n, k0:k0+nb) in place with partial pivoting; piv[j] = chosen row for column k0+j.
+__global__ void __launch_bounds__(1024) lu_panel_kernel(int n, int k0, int nb, double* __restrict__ A,
+                                                        int32_t* __restrict__ piv, int32_t* __restrict__ info) {
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_p;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    for (int j = 0; j < nb; ++j) {
+        const int col = k0 + j;
+        double best = -1.0;
+        int bi = col;
+        for (int i = col + tid; i < n; i += nt) {
+            const double v = fabs(A[(size_t)i * n + col]);
+            if (v > best) {
+                best = v;
+                bi = i;
+            }
+        }
+        warp_argmax(best, bi);
+        if (lane == 0) {
+            s_val[warp] = best;
+            s_idx[warp] = bi;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < nw ? s_val[lane] : -1.0;
+            bi = lane < nw ? s_idx[lane] : 0x7fffffff;
+            warp_argmax(best, bi);
+            if (lane == 0) {
+                s_p = bi;
+                piv[j] = bi;
+                if (best == 0.0 && *info == 0) *info = col + 1;
+            }
+        }
+        __syncthreads();
+        const int p = s_p;
+        if (p != col && tid < nb) {  // swap inside the panel only; the rest is swapped by lu_swap_trsm_kernel
+            const double t = A[(size_t)col * n + k0 + tid];
+            A[(size_t)col * n + k0 + tid] = A[(size_t)p * n + k0 + tid];
+            A[(size_t)p * n + k0 + tid] = t;
+        }
+        __syncthreads();
+        const double pv = A[(size_t)col * n + col];
+        if (pv != 0.0) {
+            // one warp per row: lane c updates column col+1+c of the panel
+            for (int i = col + 1 + warp; i < n; i += nw) {
+                double l = 0.0;
+                if (lane == 0) {
+                    l = A[(size_t)i * n + col] / pv;
+                    A[(size_t)i * n + col] = l;
+                }
+                l = __shfl_sync(0xffffffffu, l, 0);
+                const int c = col + 1 + lane;
+                if (c < k0 + nb) A[(size_t)i * n + c] = fma(-l, A[(size_t)col * n + c], A[(size_t)i * n + c]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Apply the panel's row swaps to the columns outside the panel (and to b), then solve
+// L11 * U12 = A12 for the columns right of the panel (and for b's top block).
+__global__ void lu_swap_trsm_kernel(int n, int k0, int nb, double* __restrict__ A, double* __restrict__ b,
+                                    const int32_t* __restrict__ piv) {
+    const int c0 = blockIdx.x * blockDim.x + threadIdx.x;  // column index over [0, n] without the panel
+    if (c0 > n - nb) return;
+    const int c = c0 < k0 ? c0 : c0 + nb;  // c == n is the right-hand side
+    auto at = [&](int r) -> double& { return c == n ? b[r] : A[(size_t)r * n + c]; };
+    for (int j = 0; j < nb; ++j) {
+        const int p = piv[j];
+        if (p != k0 + j) {
+            const double t = at(k0 + j);
+            at(k0 + j) = at(p);
+            at(p) = t;
+        }
+    }
+    if (c < k0) return;
+    for (int j = 1; j < nb; ++j) {  // unit lower triangular forward substitution
+        double acc = at(k0 + j);
+        for (int q = 0; q < j; ++q) acc = fma(-A[(size_t)(k0 + j) * n + k0 + q], at(k0 + q), acc);
+        at(k0 + j) = acc;
+    }
+}
+
+// A22 -= L21 * U12 (and b2 -= L21 * y1): 64x64 output tile per CTA, K = nb <= 32.
+__global__ void __launch_bounds__(256) lu_update_kernel(int n, int k0, int nb, double* __restrict__ A,
+                                                        double* __restrict__ b) {
+    __shared__ double sL[64][NB + 1];
+    __shared__ double sU[NB][64 + 1];
+    const int r0 = k0 + nb + blockIdx.y * 64, c0 = k0 + nb + blockIdx.x * 64;  // columns run to n (inclusive: rhs)
+    const int tid = threadIdx.x;
+    for (int q = tid; q < 64 * nb; q += 256) {
+        const int i = q / nb, j = q % nb;
+        sL[i][j] = (r0 + i < n) ? A[(size_t)(r0 + i) * n + k0 + j] : 0.0;
+    }
+    for (int q = tid; q < nb * 64; q += 256) {
+        const int j = q / 64, c = q % 64;
+        const int cc = c0 + c;
+        sU[j][c] = cc < n ? A[(size_t)(k0 + j) * n + cc] : (cc == n ? b[k0 + j] : 0.0);
+    }
+    __syncthreads();
+    const int ty = tid / 16, tx = tid % 16;  // 16x16 threads, 4x4 outputs each
+    double acc[4][4] = {};
+    for (int j = 0; j < nb; ++j) {
+        double l[4], uu[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) l[a] = sL[ty * 4 + a][j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) uu[c] = sU[j][tx * 4 + c];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] = fma(l[a], uu[c], acc[a][c]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int r = r0 + ty * 4 + a;
+        if (r >= n) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int cc = c0 + tx * 4 + c;
+            if (cc < n)
+                A[(size_t)r * n + cc] -= acc[a][c];
+            else if (cc == n)
+                b[r] -= acc[a][c];
+        }
+    }
+}
+
+// x = U^{-1} y in place (column oriented, one CTA)
+__global__ void __launch_bounds__(1024) lu_backsolve_kernel(int n, const double* __restrict__ A,
+                                                            double* __restrict__ b) {
+    __shared__ double s_x;
+    for (int i = n - 1; i >= 0; --i) {
+        if (threadIdx.x == 0) {
+            const double d = A[(size_t)i * n + i];
+            s_x = d != 0.0 ? b[i] / d : b[i];
+            b[i] = s_x;
+        }
+        __syncthreads();
+        const double xi = s_x;
+        for (int r = threadIdx.x; r < i; r += blockDim.x) b[r] = fma(-A[(size_t)r * n + i], xi, b[r]);
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" int pf_solve_dense(int64_t nbatch, int64_t n, double* A, double* b, int32_t* info, void* stream) {
+    PF_REQUIRE(nbatch >= 1 && n >= 1, "pf_solve_dense: nbatch and n must be >= 1");
+    PF_REQUIRE(A && b && info, "pf_solve_dense: NULL argument");
+    PF_REQUIRE(n < (1 << 15), "pf_solve_dense: n too large (%lld)", (long long)n);
+    cudaStream_t st = pf_stream_of(stream);
+    if (n <= kSmallMax) {
+        const int ld = (int)n + 1 + ((int)n & 1);
+        const size_t smem = (size_t)n * ld * sizeof(double);
+        if (smem > 48 * 1024)
+            PF_CUDA_CHECK(cudaFuncSetAttribute(lu_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lu_small_kernel<<<(unsigned)nbatch, 128, smem, st>>>((int)n, A, b, info);
+        PF_CUDA_CHECK(cudaGetLastError());
+        return PF_OK;
+    }
+    int32_t* piv = nullptr;
+    PF_CUDA_CHECK(cudaMallocAsync((void**)&piv, NB * sizeof(int32_t), st));
+    PF_CUDA_CHECK(cudaMemsetAsync(info, 0, nbatch * sizeof(int32_t), st));
+    for (int64_t m = 0; m < nbatch; ++m) {
+        double* Am = A + (size_t)m * n * n;
+        double* bm = b + (size_t)m * n;
+        for (int k0 = 0; k0 < (int)n; k0 += NB) {
+            const int nb = std::min<int>(NB, (int)n - k0);
+            lu_panel_kernel<<<1, 1024, 0, st>>>((int)n, k0, nb, Am, piv, info + m);
+            const int ncols = (int)n + 1 - nb;
+            lu_swap_trsm_kernel<<<(ncols + 127) / 128, 128, 0, st>>>((int)n, k0, nb, Am, bm, piv);
+            const int rem = (int)n - k0 - nb;
+            if (rem > 0) {
+                dim3 grid((rem + 1 + 63) / 64, (rem + 63) / 64);
+                lu_update_kernel<<<grid, 256, 0, st>>>((int)n, k0, nb, Am, bm);
+            }
+        }
+        lu_backsolve_kernel<<<1, 1024, 0, st>>>((int)n, Am, bm);
+    }
+    PF_CUDA_CHECK(cudaGetLastError());
+    PF_CUDA_CHECK(cudaFreeAsync(piv, st));
+    return PF_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Jacobi-preconditioned conjugate gradients, matrix-free, batched over problems
+// ---------------------------------------------------------------------------------------
+namespace {
+
+constexpr int CG_BX = 32, CG_BY = 8, CG_RPT = 32;  // a CTA covers 256 rows x 32 problems
+constexpr int CG_TILE_ROWS = CG_BY * CG_RPT;
+
+struct CgVec {
+    const uint8_t* __restrict__ dof_free;
+    int64_t ndof, B;
+};
+
+// per-column partial sums of a*b over the CTA's rows (fixed order) -> part[blockIdx.x][b]
+__device__ __forceinline__ void cg_block_reduce(double acc, double* __restrict__ part, int64_t B, int64_t b) {
+    __shared__ double s[CG_BY][CG_BX];
+    s[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && b < B) {
+        double t = 0.0;
+        for (int y = 0; y < CG_BY; ++y) t += s[y][threadIdx.x];
+        part[(int64_t)blockIdx.x * B + b] = t;
+    }
+    __syncthreads();
+}
+
+// dinv = 1 / diag(K) on free DOFs (0 on fixed): node-centric, linear element
+template <int DIM>
+__global__ void cg_diag_kernel(const int32_t* __restrict__ inc_ptr, const PfIncidence* __restrict__ inc,
+                               const double4* __restrict__ inc_geo, const uint8_t* __restrict__ dof_free,
+                               const double* __restrict__ E, const double* __restrict__ A, int64_t mat_stride,
+                               int64_t mat_bmul, int64_t nnode, int64_t B, double* __restrict__ dinv) {
+    const int64_t b = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    const int64_t n = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    if (b >= B || n >= nnode) return;
+    double dx = 0.0, dy = 0.0;
+    for (int k = inc_ptr[n]; k < inc_ptr[n + 1]; ++k) {
+        const PfIncidence ic = inc[k];
+        const double4 g = inc_geo[k];
+        const double kk = E[(int64_t)ic.elem * mat_stride + b * mat_bmul] * A[(int64_t)ic.elem * mat_stride + b * mat_bmul] * g.z;
+        dx += kk * (DIM == 2 ? g.x * g.x : 1.0);
+        dy += kk * g.y * g.y;
+    }
+    const int64_t d0 = n * DIM;
+    dinv[d0 * B + b] = (dof_free[d0] && dx != 0.0) ? 1.0 / dx : 0.0;
+    if (DIM == 2) dinv[(d0 + 1) * B + b] = (dof_free[d0 + 1] && dy != 0.0) ? 1.0 / dy : 0.0;
+}
+
+// r = mask*rhs, x = 0, p = z = dinv*r; partial sums of r.z and rhs.rhs
+__global__ void cg_init_kernel(CgVec v, const double* __restrict__ rhs, const double* __restrict__ dinv,
+                               double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
+                               double* __restrict__ part_rz, double* __restrict__ part_bb) {
+    const int64_t b = (int64_t)blockIdx.y * CG_BX + threadIdx.x;
+    double rz = 0.0, bb = 0.0;
+    for (int t = 0; t < CG_RPT; ++t) {
+        const int64_t d = ((int64_t)blockIdx.x * CG_BY + threadIdx.y) * CG_RPT + t;
+        if (d < v.ndof && b < v.B) {
+            const int64_t q = d * v.B + b;
+            const double rr = v.dof_free[d] ? rhs[q] : 0.0;
+            const double z = dinv[q] * rr;
+            x[q] = 0.0;
+            r[q] = rr;
+            p[q] = z;
+            rz += rr * z;
+            bb += rr * rr;
+        }
+    }
+    cg_block_reduce(rz, part_rz, v.B, b);
+    cg_block_reduce(bb, part_bb, v.B, b);
+}
+
+__global__ void cg_dot_kernel(CgVec v, const double* __restrict__ p, const double* __restrict__ Ap,
+                              double* __restrict__ part) {
+    const int64_t b = (int64_t)blockIdx.y * CG_BX + threadIdx.x;
+    double acc = 0.0;
+    for (int t = 0; t < CG_RPT; ++t) {
+        const int64_t d = ((int64_t)blockIdx.x * CG_BY + threadIdx.y) * CG_RPT + t;
+        if (d < v.ndof && b < v.B && v.dof_free[d]) acc += p[d * v.B + b] * Ap[d * v.B + b];
+    }
+    cg_block_reduce(acc, part, v.B, b);
+}
+
+// x += alpha p; r -= alpha Ap (free rows); partial sums of r.z (z = dinv r) and r.r
+__global__ void cg_update_kernel(CgVec v, const double* __restrict__ rz, const double* __restrict__ pAp,
+                                 const double* __restrict__ p, const double* __restrict__ Ap,
+                                 const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
+                                 double* __restrict__ part_rz, double* __restrict__ part_rr) {
+    const int64_t b = (int64_t)blockIdx.y * CG_BX + threadIdx.x;
+    double alpha = 0.0;
+    if (b < v.B && pAp[b] != 0.0) alpha = rz[b] / pAp[b];
+    double s_rz = 0.0, s_rr = 0.0;
+    for (int t = 0; t < CG_RPT; ++t) {
+        const int64_t d = ((int64_t)blockIdx.x * CG_BY + threadIdx.y) * CG_RPT + t;
+        if (d < v.ndof && b < v.B && v.dof_free[d]) {
+            const int64_t q = d * v.B + b;
+            x[q] = fma(alpha, p[q], x[q]);
+            const double rr = fma(-alpha, Ap[q], r[q]);
+            r[q] = rr;
+            s_rz += rr * (dinv[q] * rr);
+            s_rr += rr * rr;
+        }
+    }
+    cg_block_reduce(s_rz, part_rz, v.B, b);
+    cg_block_reduce(s_rr, part_rr, v.B, b);
+}
+
+// p = z + (rz_new / rz) p
+__global__ void cg_direction_kernel(CgVec v, const double* __restrict__ rz_new, const double* __restrict__ rz,
+                                    const double* __restrict__ r, const double* __restrict__ dinv,
+                                    double* __restrict__ p) {
+    const int64_t b = (int64_t)blockIdx.y * CG_BX + threadIdx.x;
+    double beta = 0.0;
+    if (b < v.B && rz[b] != 0.0) beta = rz_new[b] / rz[b];
+    for (int t = 0; t < CG_RPT; ++t) {
+        const int64_t d = ((int64_t)blockIdx.x * CG_BY + threadIdx.y) * CG_RPT + t;
+        if (d < v.ndof && b < v.B) {
+            const int64_t q = d * v.B + b;
+            p[q] = v.dof_free[d] ? fma(beta, p[q], dinv[q] * r[q]) : 0.0;
+        }
+    }
+}
+
+__global__ void cg_colsum_kernel(const double* __restrict__ part, int64_t rows, int64_t B, double* __restrict__ out) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double acc = 0.0;
+    for (int64_t r = 0; r < rows; ++r) acc += part[r * B + b];
+    out[b] = acc;
+}
+
+}  // namespace
+
+extern "C" int64_t pf_cg_work_len(const pf_plan* plan, int64_t B) {
+    if (!plan || B < 1) return -1;
+    const int64_t tiles = (plan->ndof + CG_TILE_ROWS - 1) / CG_TILE_ROWS;
+    return 4 * plan->ndof * B + 2 * tiles * B + 8 * B;
+}
+
+extern "C" int pf_cg_solve(pf_plan* plan, int kind, int64_t B, const double* u, const double* E, const double* A,
+                           int mat_batched, const double* rhs, double* x, double rel_tol, int max_iters,
+                           double* work, int64_t work_len, int32_t* iters_out, double* resid_out, void* stream) {
+    int rc = pf_plan_activate(plan);
+    if (rc) return rc;
+    PF_REQUIRE(kind == PF_ELEM_LINEAR || plan->dim == 1, "pf_cg_solve: linear element only");
+    PF_REQUIRE(B >= 1 && E && A && rhs && x && work, "pf_cg_solve: bad argument");
+    PF_REQUIRE(work_len >= pf_cg_work_len(plan, B), "pf_cg_solve: work buffer too small");
+    cudaStream_t st = pf_stream_of(stream);
+    const int64_t nd = plan->ndof, tiles = (nd + CG_TILE_ROWS - 1) / CG_TILE_ROWS;
+    double* r = work;
+    double* p = r + nd * B;
+    double* Ap = p + nd * B;
+    double* dinv = Ap + nd * B;
+    double* part0 = dinv + nd * B;
+    double* part1 = part0 + tiles * B;
+    double* rz = part1 + tiles * B;
+    double* pAp = rz + B;
+    double* rz_new = pAp + B;
+    double* bb = rz_new + B;
+    double* rr = bb + B;
+    CgVec v{plan->d_dof_free, nd, B};
+    dim3 blk(CG_BX, CG_BY), grd((unsigned)tiles, (unsigned)((B + CG_BX - 1) / CG_BX));
+    const unsigned cb = (unsigned)((B + 127) / 128);
+    {
+        dim3 dblk(32, 8), dgrd((unsigned)((plan->nnode + 7) / 8), (unsigned)((B + 31) / 32));
+        const int64_t ms = mat_batched ? B : 1, mb = mat_batched ? 1 : 0;
+        if (plan->dim == 1)
+            cg_diag_kernel<1><<<dgrd, dblk, 0, st>>>(plan->d_inc_ptr, plan->d_inc, plan->d_inc_geo, plan->d_dof_free, E, A, ms, mb, plan->nnode, B, dinv);
+        else
+            cg_diag_kernel<2><<<dgrd, dblk, 0, st>>>(plan->d_inc_ptr, plan->d_inc, plan->d_inc_geo, plan->d_dof_free, E, A, ms, mb, plan->nnode, B, dinv);
+    }
+    cg_init_kernel<<<grd, blk, 0, st>>>(v, rhs, dinv, x, r, p, part0, part1);
+    cg_colsum_kernel<<<cb, 128, 0, st>>>(part0, tiles, B, rz);
+    cg_colsum_kernel<<<cb, 128, 0, st>>>(part1, tiles, B, bb);
+    PF_CUDA_CHECK(cudaGetLastError());
+    std::vector<double> h_rr(B), h_bb(B);
+    PF_CUDA_CHECK(cudaMemcpyAsync(h_bb.data(), bb, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PF_CUDA_CHECK(cudaStreamSynchronize(st));
+    int it = 0;
+    double worst = 0.0;
+    bool done = true;
+    for (int64_t b = 0; b < B; ++b) done = done && h_bb[b] == 0.0;
+    while (!done && it < max_iters) {
+        rc = pf_tangent_matvec(plan, kind, B, u, E, A, mat_batched, p, Ap, stream);
+        if (rc) return rc;
+        cg_dot_kernel<<<grd, blk, 0, st>>>(v, p, Ap, part0);
+        cg_colsum_kernel<<<cb, 128, 0, st>>>(part0, tiles, B, pAp);
+        cg_update_kernel<<<grd, blk, 0, st>>>(v, rz, pAp, p, Ap, dinv, x, r, part0, part1);
+        cg_colsum_kernel<<<cb, 128, 0, st>>>(part0, tiles, B, rz_new);
+        cg_colsum_kernel<<<cb, 128, 0, st>>>(part1, tiles, B, rr);
+        cg_direction_kernel<<<grd, blk, 0, st>>>(v, rz_new, rz, r, dinv, p);
+        std::swap(rz, rz_new);
+        ++it;
+        if (it % 8 == 0 || it == max_iters) {
+            PF_CUDA_CHECK(cudaMemcpyAsync(h_rr.data(), rr, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+            PF_CUDA_CHECK(cudaStreamSynchronize(st));
+            done = true;
+            worst = 0.0;
+            for (int64_t b = 0; b < B; ++b) {
+                const double rel = h_bb[b] > 0.0 ? std::sqrt(h_rr[b] / h_bb[b]) : 0.0;
+                worst = std::max(worst, rel);
+                if (!(rel <= rel_tol)) done = false;
+            }
+        }
+    }
+    PF_CUDA_CHECK(cudaGetLastError());
+    if (iters_out) *iters_out = it;
+    if (resid_out) *resid_out = worst;
+    return PF_OK;
+}

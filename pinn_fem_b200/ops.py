@@ -166,3 +166,76 @@ def gd_solve(plan: AssemblyPlan, nets: Sequence[Optional[NetSpec]], scales: Sequ
                                       _ptr(f_ext), _ptr(md), _ptr(mv), _ptr(history), _ptr(n_iters), _ptr(converged),
                                       _ptr(reactions), _stream_ptr(dev)))
     return GDResult(u=u, theta=theta, reactions=reactions, history=history, n_iters=n_iters, converged=converged)
+
+
+def solve_dense(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Solve ``A x = b`` by LU with partial pivoting (np.linalg.solve / torch.linalg.solve
+    in the reference).  ``A`` is ``[n, n]`` or ``[batch, n, n]``; both inputs are left
+    untouched.  Raises ``RuntimeError("Singular matrix")`` on an exactly zero pivot."""
+    A = _dev_f64(A, "A")
+    b = _dev_f64(b, "b")
+    batched = A.dim() == 3
+    A3 = (A if batched else A.unsqueeze(0)).clone()
+    x = (b if batched else b.unsqueeze(0)).clone()
+    nb, n = A3.shape[0], A3.shape[1]
+    if A3.shape[2] != n or tuple(x.shape) != (nb, n):
+        raise ValueError("solve_dense: shape mismatch")
+    info = torch.zeros(nb, dtype=torch.int32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(_lib.load().pf_solve_dense(nb, n, _ptr(A3), _ptr(x), _ptr(info), _stream_ptr(A.device)))
+    if bool((info != 0).any()):
+        raise RuntimeError("Singular matrix")
+    return x if batched else x[0]
+
+
+def cg_solve(plan: AssemblyPlan, E, A, rhs, u=None, kind="linear", rel_tol=1e-10, max_iters=10000):
+    """Jacobi-preconditioned CG on the free DOFs of ``K(E, A) x = rhs`` (matrix-free,
+    batched ``[ndof, B]``).  Returns ``(x, iterations, worst relative residual)``."""
+    from .plan import KINDS
+
+    plan._need_device()
+    B = plan._chk(rhs, plan.ndof, "rhs")
+    mb = plan._materials(E, A, B)
+    lib = _lib.load()
+    work = torch.empty(int(lib.pf_cg_work_len(plan._handle, B)), dtype=torch.float64, device=plan.device)
+    x = torch.empty_like(rhs)
+    iters, resid = C.c_int32(0), C.c_double(0.0)
+    with torch.cuda.device(plan.device):
+        check(lib.pf_cg_solve(plan._handle, KINDS[kind], B, _ptr(u), _ptr(E), _ptr(A), mb, _ptr(rhs), _ptr(x),
+                              float(rel_tol), int(max_iters), _ptr(work), work.numel(), C.byref(iters),
+                              C.byref(resid), _stream_ptr(plan.device)))
+    return x, int(iters.value), float(resid.value)
+
+
+def gn_jacobian(plan: AssemblyPlan, u, E, A, jacE=None, jacA=None, n_rest=0, alpha_physics=1.0, alpha_data=1.0,
+                meas_dofs=None) -> torch.Tensor:
+    """Stacked Gauss-Newton Jacobian ``[(nfree + n_meas), nfree + nE + nA + n_rest]``
+    (fem/nn_solver.py:50-135, :223-239) assembled in closed form on the device."""
+    plan._need_device()
+    dev = plan.device
+    vals = plan.tangent_bsr(E, A)
+    nE = 0 if jacE is None else jacE.shape[1]
+    nA = 0 if jacA is None else jacA.shape[1]
+    md = None if meas_dofs is None else torch.as_tensor(meas_dofs, device=dev).to(torch.int32).contiguous()
+    n_meas = 0 if md is None else md.numel()
+    J = torch.empty((plan.nfree + n_meas, plan.nfree + nE + nA + n_rest), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().pf_gn_jacobian(plan._handle, _lib.ELEM_LINEAR, _ptr(u), _ptr(E), _ptr(A), _ptr(vals),
+                                         _ptr(jacE), nE, _ptr(jacA), nA, int(n_rest), float(alpha_physics),
+                                         float(alpha_data), _ptr(md), n_meas, _ptr(J), _stream_ptr(dev)))
+    return J
+
+
+def gn_normal_equations(J: torch.Tensor, R: torch.Tensor, damping_factor: float = 1e-6):
+    """``JtJ + d I`` with ``d = damping_factor * trace(JtJ) / n``, ``Jtr`` and ``d``
+    (fem/nn_solver.py:268-274); J^T J runs on the fp64 tensor cores (DMMA)."""
+    J = _dev_f64(J, "J")
+    R = _dev_f64(R, "R")
+    m, n = J.shape
+    jtj = torch.empty((n, n), dtype=torch.float64, device=J.device)
+    jtr = torch.empty(n, dtype=torch.float64, device=J.device)
+    damping = torch.empty(1, dtype=torch.float64, device=J.device)
+    with torch.cuda.device(J.device):
+        check(_lib.load().pf_gn_normal_equations(m, n, _ptr(J), _ptr(R), float(damping_factor), _ptr(jtj), _ptr(jtr),
+                                                 _ptr(damping), _stream_ptr(J.device)))
+    return jtj, jtr, damping
