@@ -138,6 +138,11 @@ int pf_material_vjp(pf_plan* plan, int kind, int64_t B, const double* u, const d
 int pf_tangent_bsr(pf_plan* plan, int kind, int64_t B, const double* u, const double* E, const double* A,
                    int mat_batched, double* vals, void* stream);
 
+/* Signed strain per element, strain dev [nelem][B]: measure 0 = small-strain axial
+ * (fem/element.py:36,:69), 1 = Green-Lagrange (fem/element.py:126), 2 = engineering
+ * (L - L0)/L0 from the deformed length (api_fem_solver.py:100-108). */
+int pf_element_strain(pf_plan* plan, int measure, int64_t B, const double* u, double* strain, void* stream);
+
 /* Dense views for the reference's dense-K callers (small meshes, B = 1):
  *   K_dense dev [ndof][ndof] row-major  (assemble_system's first return value)
  *   K_ff    dev [nfree][nfree]          (K[np.ix_(free, free)], fem/core.py:32) */
@@ -194,7 +199,9 @@ typedef struct pf_gd_config {
     int32_t net_width[3];
     double net_scale[3];
     int32_t n_measured;
-    int32_t reserved;
+    /* 0: fem/solver.py losses (0.5*sum r^2, converge on ||r|| or loss);
+     * 1: legacy fem/nn_solver_gd.py:113-124,:171 (mean r^2, converge on loss only) */
+    int32_t loss_mode;
 } pf_gd_config;
 
 #define PF_GD_HISTORY_COLS 7 /* iteration, loss_total, loss_physics, loss_data, u_norm, residual_norm, theta_norm */

@@ -47,7 +47,7 @@ class GDConfig(C.Structure):
         ("net_width", C.c_int32 * 3),
         ("net_scale", C.c_double * 3),
         ("n_measured", C.c_int32),
-        ("reserved", C.c_int32),
+        ("loss_mode", C.c_int32),
     ]
 
 
@@ -69,6 +69,7 @@ SIGNATURES = {
     "pf_tangent_matvec": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "pf_material_vjp": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
     "pf_tangent_bsr": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _int, _vp, _vp]),
+    "pf_element_strain": (_int, [_vp, _int, _i64, _vp, _vp, _vp]),
     "pf_bsr_to_dense": (_int, [_vp, _vp, _vp, _vp]),
     "pf_bsr_to_free_dense": (_int, [_vp, _vp, _vp, _vp]),
     "pf_mlp_num_params": (_i64, [_int, _int, _int]),

@@ -445,6 +445,33 @@ __global__ void __launch_bounds__(kMaxBlockThreads) tangent_bsr_kernel(TangentAr
     }
 }
 
+// signed strain per element: measure 0 = small-strain axial (fem/element.py:69), 1 = Green-Lagrange
+// (element.py:126), 2 = engineering (L - L0)/L0 from the deformed length (api_fem_solver.py:100-108)
+template <int DIM>
+__global__ void element_strain_kernel(const int2* __restrict__ conn, const double4* __restrict__ elem_geo,
+                                      const double4* __restrict__ elem_xy, const double* __restrict__ u, int measure,
+                                      int64_t nelem, int64_t B, double* __restrict__ out) {
+    const int64_t b = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    if (b >= B || e >= nelem) return;
+    const int2 c = conn[e];
+    const double4 geo = elem_geo[e];
+    const Vec2 ui = load_vec2<DIM>(u, c.x, B, b), uj = load_vec2<DIM>(u, c.y, B, b);
+    double eps;
+    if (measure == 0 || DIM == 1) {
+        eps = DIM == 2 ? (geo.x * (uj.x - ui.x) + geo.y * (uj.y - ui.y)) * geo.z : (uj.x - ui.x) * geo.z;
+    } else {
+        const double4 xy = elem_xy[e];
+        const double dx = (xy.z + uj.x) - (xy.x + ui.x), dy = (xy.w + uj.y) - (xy.y + ui.y);
+        const double l0 = geo.w;
+        if (measure == 1)
+            eps = (dx * dx + dy * dy - l0 * l0) / (2.0 * l0 * l0);
+        else
+            eps = (sqrt(dx * dx + dy * dy) - l0) / l0;
+    }
+    out[e * B + b] = eps;
+}
+
 template <int DIM>
 __global__ void bsr_to_dense_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                                     const double* __restrict__ vals, int64_t nnode, int64_t ld,
@@ -713,4 +740,22 @@ extern "C" int pf_bsr_to_dense(pf_plan* plan, const double* vals, double* K_dens
 
 extern "C" int pf_bsr_to_free_dense(pf_plan* plan, const double* vals, double* K_ff, void* stream) {
     return bsr_dense(plan, vals, K_ff, true, pf_stream_of(stream));
+}
+
+extern "C" int pf_element_strain(pf_plan* plan, int measure, int64_t B, const double* u, double* strain, void* stream) {
+    int rc = pf_plan_activate(plan);
+    if (rc) return rc;
+    PF_REQUIRE(measure >= 0 && measure <= 2, "unknown strain measure %d", measure);
+    PF_REQUIRE(B >= 1 && u && strain, "pf_element_strain: bad argument");
+    if (plan->nelem == 0) return PF_OK;
+    dim3 block;
+    pick_block(B, block);
+    dim3 grid((unsigned)((plan->nelem + block.y - 1) / block.y), (unsigned)((B + block.x - 1) / block.x), 1);
+    cudaStream_t st = pf_stream_of(stream);
+    if (plan->dim == 1)
+        element_strain_kernel<1><<<grid, block, 0, st>>>(plan->d_conn, plan->d_elem_geo, plan->d_elem_xy, u, measure, plan->nelem, B, strain);
+    else
+        element_strain_kernel<2><<<grid, block, 0, st>>>(plan->d_conn, plan->d_elem_geo, plan->d_elem_xy, u, measure, plan->nelem, B, strain);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return PF_OK;
 }

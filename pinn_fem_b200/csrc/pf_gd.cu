@@ -41,7 +41,7 @@ struct GdArgs {
     const PfIncidence* __restrict__ inc;
     const double4* __restrict__ inc_geo;
     const uint8_t* __restrict__ dof_free;
-    int dim, nnode, nelem, ndof;
+    int dim, nnode, nelem, ndof, nfree;
     // problems
     double* theta;
     double* u;
@@ -182,10 +182,12 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
         nets_forward(a, sm);
         gather_linear(a, sm, u, sm + a.o_f);
         __syncthreads();
+        const bool legacy = cfg.loss_mode == 1;  // fem/nn_solver_gd.py: mean-squared physics loss
+        const double gscale = legacy ? 2.0 * cfg.alpha_physics / (double)a.nfree : cfg.alpha_physics;
         for (int d = tid; d < a.ndof; d += nt) {
             const double rr = a.dof_free[d] ? __dsub_rn(sm[a.o_f + d], __dmul_rn(lam, sm[a.o_fext + d])) : 0.0;
             r[d] = rr;
-            gf[d] = cfg.alpha_physics * rr;  // dL/df_int
+            gf[d] = gscale * rr;  // dL/df_int
         }
         __syncthreads();
         // ---- losses (solver.py:270-283): warp 0 reduces in a fixed order ----
@@ -202,9 +204,9 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
                 sd = warp_sum(sd) / cfg.n_measured;
             }
             if (lane == 0) {
-                red[0] = 0.5 * s;                                          // loss_physics
+                red[0] = legacy ? s / (double)a.nfree : 0.5 * s;          // loss_physics
                 red[1] = sd;                                               // loss_data
-                red[2] = cfg.alpha_physics * (0.5 * s) + (has_meas ? cfg.alpha_data * sd : 0.0);  // loss_total
+                red[2] = cfg.alpha_physics * red[0] + (has_meas ? cfg.alpha_data * sd : 0.0);  // loss_total
                 red[3] = sqrt(s);                                          // ||r||
             }
         }
@@ -360,8 +362,8 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
                 h[6] = tn;
             }
             int c = 0;
-            if (it > 10) {  // solver.py:341-355
-                if (red[3] < cfg.tolerance) c = 1;
+            if (it > 10) {  // solver.py:341-355 (legacy nn_solver_gd.py:171: loss only)
+                if (cfg.loss_mode == 0 && red[3] < cfg.tolerance) c = 1;
                 else if (!isnan(red[2]) && red[2] < cfg.tolerance) c = 1;
             }
             red[5] = (double)c;
@@ -416,6 +418,7 @@ extern "C" int pf_gd_solve(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob
     a.nnode = (int)plan->nnode;
     a.nelem = (int)plan->nelem;
     a.ndof = (int)plan->ndof;
+    a.nfree = (int)plan->nfree;
     a.theta = theta;
     a.u = u;
     a.f_ext = f_ext;

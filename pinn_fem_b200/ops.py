@@ -104,7 +104,7 @@ class GDResult:
 def gd_solve(plan: AssemblyPlan, nets: Sequence[Optional[NetSpec]], scales: Sequence[float], theta, u, f_ext,
              meas_dofs=None, meas_vals=None, *, max_iterations=1000, tolerance=1e-6, learning_rate_u=1e-7,
              learning_rate_theta=1e-4, alpha_physics=1.0, alpha_data=100.0, load_factor=1.0,
-             record_history=True) -> GDResult:
+             record_history=True, legacy_loss=False) -> GDResult:
     """Run ``solve_gd``'s inner loop (fem/solver.py:252-355) on the device for ``nprob``
     independent problems sharing ``plan``.  ``nets[k]`` is the architecture of
     property k (young, area, density) or None for a scalar of value ``scales[k]``;
@@ -127,6 +127,7 @@ def gd_solve(plan: AssemblyPlan, nets: Sequence[Optional[NetSpec]], scales: Sequ
     cfg.alpha_physics = float(alpha_physics)
     cfg.alpha_data = float(alpha_data)
     cfg.load_factor = float(load_factor)
+    cfg.loss_mode = 1 if legacy_loss else 0
     ntheta = 0
     for k in range(3):
         spec = nets[k] if k < len(nets) else None

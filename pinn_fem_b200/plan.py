@@ -226,6 +226,16 @@ class AssemblyPlan:
                                            _stream_ptr(self.device)))
         return vals
 
+    def element_strain(self, u, measure="linear") -> torch.Tensor:
+        """Signed strain per element ``[nelem(, B)]``: "linear", "green_lagrange" or "engineering"."""
+        self._need_device()
+        B = self._chk(u, self.ndof, "u")
+        m = {"linear": 0, "green_lagrange": 1, "gl": 1, "engineering": 2}[measure]
+        out = torch.empty((self.nelem,) if u.dim() == 1 else (self.nelem, B), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.pf_element_strain(self._handle, m, B, _ptr(u), _ptr(out), _stream_ptr(self.device)))
+        return out
+
     def bsr_to_dense(self, vals, free_only: bool = False) -> torch.Tensor:
         self._need_device()
         n = self.nfree if free_only else self.ndof
