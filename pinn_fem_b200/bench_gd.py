@@ -1,0 +1,71 @@
+"""Secondary benchmark metric: PINN-GD iterations per second (BASELINE.json configs[1]).
+
+Workload: the example 4-P model (4-node bar, 3 elements, E/A/rho = three tanh MLPs with
+521/316/161 parameters, 6 measured DOFs, Adam on u and theta) -- every iteration is the
+full fem/solver.py:252-355 loop body including the history row.  ``single`` runs one
+problem (the reference's use case: latency bound), ``batched`` runs 512 independent
+inverse problems per GPU (one CTA each), the batch-sharded configuration of BASELINE.json."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .plan import AssemblyPlan
+
+NODES = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0], [3.0, 0.0]])
+ELEMENTS = np.array([[0, 1], [1, 2], [2, 3]])
+FIXED = np.array([0, 1, 3, 5, 7])
+LOADS = np.array([0.0, 0, 0, 0, 0, 0, 1.0, 0])
+MEAS_DOFS = np.array([2, 3, 4, 5, 6, 7])
+MEAS_VALS = np.array([1.0, 0, 2, 0, 3, 0])
+
+
+def _theta0(nprob, device, seed=0):
+    from .examples.json.generic import SimpleNN
+
+    torch.manual_seed(seed)
+    nets = [SimpleNN(2, w, 3) for w in (20, 15, 10)]
+    base = torch.cat([p.detach().reshape(-1) for n in nets for p in n.parameters()]).to(device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    noise = 0.01 * torch.randn((nprob, base.numel()), generator=g, device=device, dtype=torch.float64)
+    noise[0] = 0.0
+    return (base[None, :] + noise).contiguous()
+
+
+def gd_iterations_per_second(device, world=1, iters=2000, batched_problems=512, batched_iters=300):
+    plan = AssemblyPlan(NODES, ELEMENTS, FIXED, device=device)
+    nets = [ops.NetSpec(3, 2, 20), ops.NetSpec(3, 2, 15), ops.NetSpec(3, 2, 10)]
+    f_ext = torch.as_tensor(LOADS).to(device)
+    out = {"workload": "example4-P model: 3 elements, 3 MLPs (998 parameters), 6 measured DOFs, Adam on u and theta, "
+                       "history recorded; fixed iteration count (tolerance 0)", "dtype": "f64"}
+    launches = 0
+    for label, nprob, n_it in (("single", 1, iters), ("batched", batched_problems, batched_iters)):
+        kw = dict(max_iterations=n_it, tolerance=0.0, learning_rate_u=0.01, learning_rate_theta=5e-4,
+                  alpha_physics=1.0, alpha_data=100.0, load_factor=1.0)
+        best = None
+        for rep in range(3):
+            theta = _theta0(nprob, device)
+            u = torch.zeros((nprob, 8), dtype=torch.float64, device=device)
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = ops.gd_solve(plan, nets, [1.0, 1.0, 1.0], theta, u, f_ext, MEAS_DOFS, MEAS_VALS, **kw)
+            e1.record()
+            torch.cuda.synchronize(device)
+            launches += 1
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        assert int(res.n_iters.min()) == n_it
+        t = torch.tensor([best], device=device, dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[label] = {"problems_per_gpu": nprob, "iterations_per_problem": n_it, "ms": float(t.item()),
+                      "iters_per_s": world * nprob * n_it / (float(t.item()) * 1e-3),
+                      "us_per_iteration": 1e3 * float(t.item()) / n_it}
+    out["reference_iters_per_s"] = {"value": 55.0, "source": "BASELINE.md section 2: example4-P, 1874 iterations in 33.8 s "
+                                                           "on the survey container's CPU (indicative)"}
+    out["gpu_launches"] = launches
+    return out

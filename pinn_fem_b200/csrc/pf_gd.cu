@@ -58,8 +58,47 @@ struct GdArgs {
     int n_tensors;    // parameter tensors per problem
     // smem offsets (doubles)
     int o_theta, o_m, o_v, o_g, o_u, o_mu, o_vu, o_gu, o_f, o_r, o_gf, o_fext, o_gval, o_delta, o_red, o_tn;
+    // staged mesh (doubles / ints, offsets in doubles)
+    int o_incgeo, o_elemgeo, o_mvals, o_ints;
+    int ninc, wmax;
     int smem_doubles;
 };
+
+// mesh tables staged in shared memory (they are read in every phase of every iteration)
+struct MeshS {
+    const double4* inc_geo;   // [ninc]
+    const double4* elem_geo;  // [nelem]
+    const int* inc_ptr;       // [nnode+1]
+    const int2* inc;          // [ninc] {elem, nbr}
+    const int2* conn;         // [nelem]
+    const int* dof_free;      // [ndof]
+    const int* meas_dofs;     // [n_measured]
+    const int* meas_first;    // [ndof] first measurement of a DOF or -1
+    const int* meas_next;     // [n_measured] next measurement of the same DOF or -1
+    const double* mvals;      // [n_measured]
+};
+
+__device__ __forceinline__ MeshS mesh_view(const GdArgs& a, double* sm) {
+    MeshS m;
+    m.inc_geo = reinterpret_cast<const double4*>(sm + a.o_incgeo);
+    m.elem_geo = reinterpret_cast<const double4*>(sm + a.o_elemgeo);
+    m.mvals = sm + a.o_mvals;
+    const int* ip = reinterpret_cast<const int*>(sm + a.o_ints);
+    m.inc_ptr = ip;
+    ip += (a.nnode + 2) & ~1;
+    m.inc = reinterpret_cast<const int2*>(ip);
+    ip += 2 * a.ninc;
+    m.conn = reinterpret_cast<const int2*>(ip);
+    ip += 2 * a.nelem;
+    m.dof_free = ip;
+    ip += a.ndof;
+    m.meas_first = ip;
+    ip += a.ndof;
+    m.meas_dofs = ip;
+    ip += a.cfg.n_measured;
+    m.meas_next = ip;
+    return m;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -67,72 +106,83 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// forward of all active nets at every element centroid
-__device__ void nets_forward(const GdArgs& a, double* sm) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    int maxL = 0;
-    for (int k = 0; k < kMaxNets; ++k)
-        if (a.nets[k].enabled && a.nets[k].active) maxL = max(maxL, a.nets[k].d.L);
-    for (int l = 0; l < maxL; ++l) {
-        for (int k = 0; k < kMaxNets; ++k) {
-            const NetDev& n = a.nets[k];
-            if (!n.enabled || !n.active || l >= n.d.L) continue;
-            const int in = l == 0 ? n.d.in_dim : n.d.w;
-            const double* W = sm + a.o_theta + n.theta_off + n.d.w_off[l];
-            const double* b = sm + a.o_theta + n.theta_off + n.d.b_off[l];
-            const double* ain = sm + n.act_off + (l == 0 ? 0 : a.nelem * n.d.in_dim + (l - 1) * a.nelem * n.d.w);
-            double* aout = sm + n.act_off + a.nelem * n.d.in_dim + l * a.nelem * n.d.w;
-            for (int it = tid; it < a.nelem * n.d.w; it += nt) {
-                const int e = it / n.d.w, o = it % n.d.w;
-                double acc = b[o];
-                for (int i = 0; i < in; ++i) acc = fma(W[o * in + i], ain[e * in + i], acc);
-                aout[e * n.d.w + o] = tanh(acc);
-            }
-        }
-        __syncthreads();
+// dot product with four independent accumulators: the fp64 FMA dependency chain, not the
+// instruction count, is what a 20-term dot product costs in this latency-bound kernel
+__device__ __forceinline__ double dot4(const double* __restrict__ w, int ws, const double* __restrict__ x, int xs,
+                                       int n) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int i = 0;
+    for (; i + 3 < n; i += 4) {
+        a0 = fma(w[i * ws], x[i * xs], a0);
+        a1 = fma(w[(i + 1) * ws], x[(i + 1) * xs], a1);
+        a2 = fma(w[(i + 2) * ws], x[(i + 2) * xs], a2);
+        a3 = fma(w[(i + 3) * ws], x[(i + 3) * xs], a3);
     }
-    for (int k = 0; k < kMaxNets; ++k) {
-        const NetDev& n = a.nets[k];
-        if (!n.active) continue;
-        double* val = sm + n.val_off;
-        if (!n.enabled) {
-            for (int e = tid; e < a.nelem; e += nt) val[e] = n.scale;
-            continue;
-        }
-        const double* wo = sm + a.o_theta + n.theta_off + n.d.w_off[n.d.L];
-        const double bo = sm[a.o_theta + n.theta_off + n.d.b_off[n.d.L]];
-        const double* aL = sm + n.act_off + a.nelem * n.d.in_dim + (n.d.L - 1) * a.nelem * n.d.w;
-        for (int e = tid; e < a.nelem; e += nt) {
-            double z = bo;
-            for (int i = 0; i < n.d.w; ++i) z = fma(wo[i], aL[e * n.d.w + i], z);
-            val[e] = pf_mlp_output(z, n.scale, 1);
-            val[a.nelem + e] = pf_mlp_output_grad(z, n.scale, 1);
-        }
-    }
-    __syncthreads();
+    for (; i < n; ++i) a0 = fma(w[i * ws], x[i * xs], a0);
+    return (a0 + a1) + (a2 + a3);
 }
 
-// out[dof] = sum over incident elements of (E A / l0) (d . (x_self - x_other)) d  -- f_int(x) or K x
-__device__ void gather_linear(const GdArgs& a, const double* sm, const double* x, double* out) {
+__device__ __forceinline__ const double* act_ptr(const GdArgs& a, const NetDev& n, const double* sm, int l) {
+    return sm + n.act_off + (l == 0 ? 0 : a.nelem * n.d.in_dim + (l - 1) * a.nelem * n.d.w);
+}
+
+// hidden layer l of both physics nets at every element, one (net, element, neuron) item per thread
+__device__ __forceinline__ void forward_hidden(const GdArgs& a, double* sm, int l) {
+    const NetDev& n0 = a.nets[0];
+    const NetDev& n1 = a.nets[1];
+    const int c0 = (n0.enabled && l < n0.d.L) ? a.nelem * n0.d.w : 0;
+    const int c1 = (n1.enabled && l < n1.d.L) ? a.nelem * n1.d.w : 0;
+    for (int q = threadIdx.x; q < c0 + c1; q += blockDim.x) {
+        const NetDev& n = q < c0 ? n0 : n1;
+        const int qq = q < c0 ? q : q - c0;
+        const int e = qq / n.d.w, o = qq - e * n.d.w;
+        const int in = l == 0 ? n.d.in_dim : n.d.w;
+        const double* th = sm + a.o_theta + n.theta_off;
+        const double z = th[n.d.b_off[l] + o] + dot4(th + n.d.w_off[l] + o * in, 1, act_ptr(a, n, sm, l) + e * in, 1, in);
+        sm[n.act_off + a.nelem * n.d.in_dim + l * a.nelem * n.d.w + qq] = tanh(z);
+    }
+}
+
+// output layer + softplus of both nets (scalar slots just broadcast their value)
+__device__ __forceinline__ void forward_output(const GdArgs& a, double* sm) {
+    for (int q = threadIdx.x; q < 2 * a.nelem; q += blockDim.x) {
+        const NetDev& n = a.nets[q < a.nelem ? 0 : 1];
+        const int e = q < a.nelem ? q : q - a.nelem;
+        double* val = sm + n.val_off;
+        if (!n.enabled) {
+            val[e] = n.scale;
+            continue;
+        }
+        const double* th = sm + a.o_theta + n.theta_off;
+        const double z = th[n.d.b_off[n.d.L]] + dot4(th + n.d.w_off[n.d.L], 1, act_ptr(a, n, sm, n.d.L) + e * n.d.w, 1, n.d.w);
+        val[e] = pf_mlp_output(z, n.scale, 1);
+        val[a.nelem + e] = pf_mlp_output_grad(z, n.scale, 1);
+    }
+}
+
+// per node: out = sum over incident elements of (E A / l0) (d . (x_self - x_other)) d  (f_int(x) or K x)
+template <class Epilogue>
+__device__ __forceinline__ void gather_linear(const GdArgs& a, const MeshS& ms, const double* sm, const double* x,
+                                              Epilogue epi) {
     const double* E = sm + a.nets[0].val_off;
     const double* A = sm + a.nets[1].val_off;
     for (int n = threadIdx.x; n < a.nnode; n += blockDim.x) {
         double fx = 0.0, fy = 0.0;
         const double xs = a.dim == 2 ? x[2 * n] : x[n];
         const double ys = a.dim == 2 ? x[2 * n + 1] : 0.0;
-        for (int k = a.inc_ptr[n]; k < a.inc_ptr[n + 1]; ++k) {
-            const PfIncidence inc = a.inc[k];
-            const double4 geo = a.inc_geo[k];
+        for (int k = ms.inc_ptr[n]; k < ms.inc_ptr[n + 1]; ++k) {
+            const int2 inc = ms.inc[k];
+            const double4 geo = ms.inc_geo[k];
             if (a.dim == 2)
-                pf_linear_incidence<2>(E[inc.elem], A[inc.elem], geo, xs, ys, x[2 * inc.nbr], x[2 * inc.nbr + 1], fx, fy);
+                pf_linear_incidence<2>(E[inc.x], A[inc.x], geo, xs, ys, x[2 * inc.y], x[2 * inc.y + 1], fx, fy);
             else
-                pf_linear_incidence<1>(E[inc.elem], A[inc.elem], geo, xs, 0.0, x[inc.nbr], 0.0, fx, fy);
+                pf_linear_incidence<1>(E[inc.x], A[inc.x], geo, xs, 0.0, x[inc.y], 0.0, fx, fy);
         }
         if (a.dim == 2) {
-            out[2 * n] = fx;
-            out[2 * n + 1] = fy;
+            epi(2 * n, fx);
+            epi(2 * n + 1, fy);
         } else {
-            out[n] = fx;
+            epi(n, fx);
         }
     }
 }
@@ -150,9 +200,39 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
     double* red = sm + a.o_red;
     const double lam = cfg.load_factor;
     const bool has_meas = cfg.n_measured > 0 && a.meas_dofs && a.meas_vals && cfg.alpha_data > 0.0;
-    const double* mvals = a.meas_vals ? a.meas_vals + prob * cfg.n_measured : nullptr;
+    const bool legacy = cfg.loss_mode == 1;  // fem/nn_solver_gd.py: mean-squared physics loss
+    const double gscale = legacy ? 2.0 * cfg.alpha_physics / (double)a.nfree : cfg.alpha_physics;
+    const MeshS ms = mesh_view(a, sm);
 
-    // ---- load the problem into shared memory ----
+    // ---- stage the mesh tables and the problem in shared memory ----
+    {
+        double4* g1 = const_cast<double4*>(ms.inc_geo);
+        int2* i1 = const_cast<int2*>(ms.inc);
+        for (int i = tid; i < a.ninc; i += nt) {
+            g1[i] = a.inc_geo[i];
+            i1[i] = make_int2(a.inc[i].elem, a.inc[i].nbr);
+        }
+        double4* g2 = const_cast<double4*>(ms.elem_geo);
+        int2* c2 = const_cast<int2*>(ms.conn);
+        for (int i = tid; i < a.nelem; i += nt) {
+            g2[i] = a.elem_geo[i];
+            c2[i] = a.conn[i];
+        }
+        int* p1 = const_cast<int*>(ms.inc_ptr);
+        for (int i = tid; i <= a.nnode; i += nt) p1[i] = a.inc_ptr[i];
+        int* f1 = const_cast<int*>(ms.dof_free);
+        int* mf = const_cast<int*>(ms.meas_first);
+        for (int i = tid; i < a.ndof; i += nt) {
+            f1[i] = a.dof_free[i];
+            mf[i] = -1;
+        }
+        int* m1 = const_cast<int*>(ms.meas_dofs);
+        double* m2 = const_cast<double*>(ms.mvals);
+        for (int i = tid; i < cfg.n_measured; i += nt) {
+            m1[i] = a.meas_dofs[i];
+            m2[i] = a.meas_vals[prob * cfg.n_measured + i];
+        }
+    }
     for (int i = tid; i < a.ntheta; i += nt) {
         th[i] = a.theta[prob * a.ntheta + i];
         sm[a.o_m + i] = 0.0;
@@ -165,61 +245,92 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
         sm[a.o_vu + i] = 0.0;
         sm[a.o_fext + i] = a.f_ext[i];
     }
-    for (int k = 0; k < kMaxNets; ++k) {
+    for (int k = 0; k < 2; ++k) {
         const NetDev& n = a.nets[k];
-        if (!n.enabled || !n.active) continue;
+        if (!n.enabled) continue;
         double* x = sm + n.act_off;  // inputs [load_factor, centroid...]: sorted dict keys (fem/properties.py:116-125)
-        for (int it = tid; it < a.nelem * n.d.in_dim; it += nt) {
-            const int e = it / n.d.in_dim, i = it % n.d.in_dim;
-            x[it] = i == 0 ? lam : a.centroid[e * (n.d.in_dim - 1) + (i - 1)];
+        for (int q = tid; q < a.nelem * n.d.in_dim; q += nt) {
+            const int e = q / n.d.in_dim, i = q % n.d.in_dim;
+            x[q] = i == 0 ? lam : a.centroid[e * (n.d.in_dim - 1) + (i - 1)];
         }
     }
     __syncthreads();
+    if (tid == 0 && has_meas) {  // per-DOF measurement lists in ascending measurement order (DOFs may repeat)
+        int* mf = const_cast<int*>(ms.meas_first);
+        int* mn = const_cast<int*>(ms.meas_next);
+        for (int j = cfg.n_measured - 1; j >= 0; --j) {
+            mn[j] = mf[ms.meas_dofs[j]];
+            mf[ms.meas_dofs[j]] = j;
+        }
+    }
+    if (tid == 0) red[5] = 0.0;
+    __syncthreads();
+
+    int maxL = 0;
+    for (int k = 0; k < 2; ++k)
+        if (a.nets[k].enabled) maxL = max(maxL, a.nets[k].d.L);
+    const int n_active_theta = a.nets[2].enabled ? a.nets[2].theta_off : a.ntheta;  // density: grad None, never stepped
+    const double cdata = has_meas ? -2.0 * cfg.alpha_data / cfg.n_measured : 0.0;
 
     int it_done = 0, conv = 0;
-    for (int it = 0; it < cfg.max_iterations; ++it) {
-        // ---- forward: materials, internal force, residual (solver.py:262-269) ----
-        nets_forward(a, sm);
-        gather_linear(a, sm, u, sm + a.o_f);
+    double pow_b1 = 1.0, pow_b2 = 1.0;  // beta^t, updated multiplicatively
+    for (int it = 0; it <= cfg.max_iterations; ++it) {
+        // ---- forward, first layer.  Thread 0 first closes the previous iteration: history row and
+        //      convergence flag (solver.py:308-355); everyone reads the flag after the barrier. ----
+        if (tid == 0 && it > 0) {
+            double tn = 0.0;
+            for (int q = 0; q < a.n_tensors; ++q) tn += sm[a.o_tn + q];
+            if (a.history) {
+                double* h = a.history + (prob * cfg.max_iterations + (it - 1)) * PF_GD_HISTORY_COLS;
+                h[0] = (double)it;
+                h[1] = red[2];
+                h[2] = red[0];
+                h[3] = cfg.n_measured > 0 ? red[1] : 0.0;
+                h[4] = red[4];
+                h[5] = red[3];
+                h[6] = tn;
+            }
+            int c = 0;
+            if (it - 1 > 10) {  // solver.py:341-355 (legacy nn_solver_gd.py:171: loss only)
+                if (!legacy && red[3] < cfg.tolerance) c = 1;
+                else if (!isnan(red[2]) && red[2] < cfg.tolerance) c = 1;
+            }
+            red[5] = (double)c;
+        }
+        if (maxL > 0) forward_hidden(a, sm, 0);
         __syncthreads();
-        const bool legacy = cfg.loss_mode == 1;  // fem/nn_solver_gd.py: mean-squared physics loss
-        const double gscale = legacy ? 2.0 * cfg.alpha_physics / (double)a.nfree : cfg.alpha_physics;
-        for (int d = tid; d < a.ndof; d += nt) {
-            const double rr = a.dof_free[d] ? __dsub_rn(sm[a.o_f + d], __dmul_rn(lam, sm[a.o_fext + d])) : 0.0;
+        it_done = it;
+        if (red[5] != 0.0) {
+            conv = 1;
+            break;
+        }
+        if (it == cfg.max_iterations) break;
+        for (int l = 1; l < maxL; ++l) {
+            forward_hidden(a, sm, l);
+            __syncthreads();
+        }
+        forward_output(a, sm);
+        __syncthreads();
+        // ---- f_int, residual and dL/df_int in one pass (solver.py:262-270) ----
+        gather_linear(a, ms, sm, u, [&](int d, double f) {
+            const double rr = ms.dof_free[d] ? __dsub_rn(f, __dmul_rn(lam, sm[a.o_fext + d])) : 0.0;
             r[d] = rr;
-            gf[d] = gscale * rr;  // dL/df_int
-        }
+            gf[d] = gscale * rr;
+        });
         __syncthreads();
-        // ---- losses (solver.py:270-283): warp 0 reduces in a fixed order ----
-        if (warp == 0) {
-            double s = 0.0;
-            for (int d = lane; d < a.ndof; d += 32) s += r[d] * r[d];
-            s = warp_sum(s);
-            double sd = 0.0;
-            if (has_meas) {
-                for (int j = lane; j < cfg.n_measured; j += 32) {
-                    const double dd = mvals[j] - u[a.meas_dofs[j]];
-                    sd += dd * dd;
-                }
-                sd = warp_sum(sd) / cfg.n_measured;
-            }
-            if (lane == 0) {
-                red[0] = legacy ? s / (double)a.nfree : 0.5 * s;          // loss_physics
-                red[1] = sd;                                               // loss_data
-                red[2] = cfg.alpha_physics * red[0] + (has_meas ? cfg.alpha_data * sd : 0.0);  // loss_total
-                red[3] = sqrt(s);                                          // ||r||
-            }
-        }
-        // ---- reverse pass: dL/du = K g_f (+ data term), dL/dE, dL/dA ----
-        gather_linear(a, sm, gf, gu);
+        // ---- reverse pass: dL/du = K g_f + data term, dL/dE, dL/dA; the last warp reduces the losses ----
+        gather_linear(a, ms, sm, gf, [&](int d, double g) {
+            for (int j = ms.meas_first[d]; j >= 0; j = ms.meas_next[j]) g += cdata * (ms.mvals[j] - u[d]);
+            gu[d] = g;
+        });
         {
             const double* E = sm + a.nets[0].val_off;
             const double* A = sm + a.nets[1].val_off;
             double* gE = sm + a.o_gval;
             double* gA = gE + a.nelem;
             for (int e = tid; e < a.nelem; e += nt) {
-                const int2 c = a.conn[e];
-                const double4 geo = a.elem_geo[e];
+                const int2 c = ms.conn[e];
+                const double4 geo = ms.elem_geo[e];
                 double gh;
                 if (a.dim == 2) {
                     const double axial = geo.x * (u[2 * c.x] - u[2 * c.y]) + geo.y * (u[2 * c.x + 1] - u[2 * c.y + 1]);
@@ -227,101 +338,124 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
                 } else {
                     gh = geo.z * (u[c.x] - u[c.y]) * (gf[c.x] - gf[c.y]);
                 }
-                gE[e] = A[e] * gh;
-                gA[e] = E[e] * gh;
+                // dL/dz of the two output layers: dL/dvalue * dvalue/dz
+                gE[e] = A[e] * gh * (a.nets[0].enabled ? sm[a.nets[0].val_off + a.nelem + e] : 0.0);
+                gA[e] = E[e] * gh * (a.nets[1].enabled ? sm[a.nets[1].val_off + a.nelem + e] : 0.0);
+            }
+        }
+        if (warp == nwarp - 1) {
+            double s = 0.0;
+            for (int d = lane; d < a.ndof; d += 32) s += r[d] * r[d];
+            s = warp_sum(s);
+            double sd = 0.0;
+            if (has_meas) {
+                for (int j = lane; j < cfg.n_measured; j += 32) {
+                    const double dd = ms.mvals[j] - u[ms.meas_dofs[j]];
+                    sd += dd * dd;
+                }
+                sd = warp_sum(sd) / cfg.n_measured;
+            }
+            if (lane == 0) {
+                red[0] = legacy ? s / (double)a.nfree : 0.5 * s;                              // loss_physics
+                red[1] = sd;                                                                  // loss_data
+                red[2] = cfg.alpha_physics * red[0] + (has_meas ? cfg.alpha_data * sd : 0.0);  // loss_total
+                red[3] = sqrt(s);                                                             // ||r||
             }
         }
         __syncthreads();
-        if (has_meas && tid == 0) {  // d mean((m - u)^2)/du, measured DOFs may repeat: serial, ordered
-            const double c = -2.0 * cfg.alpha_data / cfg.n_measured;
-            for (int j = 0; j < cfg.n_measured; ++j) gu[a.meas_dofs[j]] += c * (mvals[j] - u[a.meas_dofs[j]]);
-        }
-        // ---- MLP backward (closed form of the autograd pass through NNProperty.value) ----
-        for (int k = 0; k < 2; ++k) {
-            const NetDev& n = a.nets[k];
-            if (!n.enabled) continue;
-            const int w = n.d.w, L = n.d.L;
-            const double* gval = sm + a.o_gval + k * a.nelem;
-            const double* sg = sm + n.val_off + a.nelem;
-            double* g = sm + a.o_g + n.theta_off;
-            const double* aL = sm + n.act_off + a.nelem * n.d.in_dim + (L - 1) * a.nelem * w;
-            const double* wo = th + n.theta_off + n.d.w_off[L];
-            double* D = sm + a.o_delta;
-            double* Dn = D + a.nelem * w;
-            for (int q = tid; q <= w; q += nt) {  // output layer: W_out[i], b_out
-                double acc = 0.0;
-                for (int e = 0; e < a.nelem; ++e) acc = fma(gval[e] * sg[e], q < w ? aL[e * w + q] : 1.0, acc);
-                g[q < w ? n.d.w_off[L] + q : n.d.b_off[L]] = acc;
+        // ---- MLP backward of both nets (closed form of autograd through NNProperty.value) ----
+        {
+            // output-layer gradients and the delta of the last hidden layer
+            int c0[2];
+            for (int k = 0; k < 2; ++k) {
+                c0[k] = a.nets[k].enabled ? a.nets[k].d.w + 1 + a.nelem * a.nets[k].d.w : 0;
             }
-            for (int q = tid; q < a.nelem * w; q += nt) {
-                const int e = q / w, o = q % w;
-                const double av = aL[q];
-                D[q] = wo[o] * (gval[e] * sg[e]) * (1.0 - av * av);
+            for (int q = tid; q < c0[0] + c0[1]; q += nt) {
+                const int k = q < c0[0] ? 0 : 1;
+                const NetDev& n = a.nets[k];
+                int qq = q - (k ? c0[0] : 0);
+                const int w = n.d.w, L = n.d.L;
+                const double* dz = sm + a.o_gval + k * a.nelem;
+                const double* aL = act_ptr(a, n, sm, L);
+                double* g = sm + a.o_g + n.theta_off;
+                if (qq < w) {
+                    g[n.d.w_off[L] + qq] = dot4(dz, 1, aL + qq, w, a.nelem);
+                } else if (qq == w) {
+                    double acc = 0.0;
+                    for (int e = 0; e < a.nelem; ++e) acc += dz[e];
+                    g[n.d.b_off[L]] = acc;
+                } else {
+                    qq -= w + 1;
+                    const int e = qq / w, o = qq - e * w;
+                    const double av = aL[qq];
+                    (sm + a.o_delta + k * 2 * a.nelem * a.wmax)[qq] = th[n.theta_off + n.d.w_off[L] + o] * dz[e] * (1.0 - av * av);
+                }
             }
             __syncthreads();
-            for (int l = L - 1; l >= 0; --l) {
-                const int in = l == 0 ? n.d.in_dim : w;
-                const double* ain = sm + n.act_off + (l == 0 ? 0 : a.nelem * n.d.in_dim + (l - 1) * a.nelem * w);
-                for (int q = tid; q < w * in + w; q += nt) {
-                    double acc = 0.0;
-                    if (q < w * in) {
-                        const int o = q / in, i = q % in;
-                        for (int e = 0; e < a.nelem; ++e) acc = fma(D[e * w + o], ain[e * in + i], acc);
-                        g[n.d.w_off[l] + q] = acc;
-                    } else {
-                        const int o = q - w * in;
+            for (int step = 0; step < maxL; ++step) {
+                // net k is at layer l = L_k - 1 - step; ping-pong delta buffers per net
+                int cnt[2];
+                for (int k = 0; k < 2; ++k) {
+                    const NetDev& n = a.nets[k];
+                    const int l = n.enabled ? n.d.L - 1 - step : -1;
+                    const int in = l == 0 ? n.d.in_dim : n.d.w;
+                    cnt[k] = l >= 0 ? n.d.w * in + n.d.w + (l > 0 ? a.nelem * n.d.w : 0) : 0;
+                }
+                for (int q = tid; q < cnt[0] + cnt[1]; q += nt) {
+                    const int k = q < cnt[0] ? 0 : 1;
+                    const NetDev& n = a.nets[k];
+                    int qq = q - (k ? cnt[0] : 0);
+                    const int w = n.d.w, l = n.d.L - 1 - step;
+                    const int in = l == 0 ? n.d.in_dim : w;
+                    const double* D = sm + a.o_delta + k * 2 * a.nelem * a.wmax + (step & 1) * a.nelem * a.wmax;
+                    double* Dn = sm + a.o_delta + k * 2 * a.nelem * a.wmax + ((step + 1) & 1) * a.nelem * a.wmax;
+                    const double* ain = act_ptr(a, n, sm, l);
+                    double* g = sm + a.o_g + n.theta_off;
+                    if (qq < w * in) {
+                        const int o = qq / in, i = qq - o * in;
+                        g[n.d.w_off[l] + qq] = dot4(D + o, w, ain + i, in, a.nelem);
+                    } else if (qq < w * in + w) {
+                        const int o = qq - w * in;
+                        double acc = 0.0;
                         for (int e = 0; e < a.nelem; ++e) acc += D[e * w + o];
                         g[n.d.b_off[l] + o] = acc;
-                    }
-                }
-                if (l > 0) {
-                    const double* W = th + n.theta_off + n.d.w_off[l];
-                    for (int q = tid; q < a.nelem * w; q += nt) {
-                        const int e = q / w, i = q % w;
-                        double acc = 0.0;
-                        for (int o = 0; o < w; ++o) acc = fma(W[o * w + i], D[e * w + o], acc);
-                        const double av = ain[q];
-                        Dn[q] = acc * (1.0 - av * av);
+                    } else {
+                        qq -= w * in + w;
+                        const int e = qq / w, i = qq - e * w;
+                        const double av = ain[qq];
+                        Dn[qq] = dot4(th + n.theta_off + n.d.w_off[l] + i, w, D + e * w, 1, w) * (1.0 - av * av);
                     }
                 }
                 __syncthreads();
-                double* tmp = D;
-                D = Dn;
-                Dn = tmp;
             }
         }
-        __syncthreads();
         // ---- two Adam steps (torch.optim.Adam defaults) and BC zeroing (solver.py:292-298) ----
         {
             const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
-            const double t = (double)(it + 1);
-            const double bc1 = 1.0 - pow(b1, t), bc2s = sqrt(1.0 - pow(b2, t));
+            pow_b1 *= b1;
+            pow_b2 *= b2;
+            const double bc1 = 1.0 - pow_b1, bc2s = sqrt(1.0 - pow_b2);
             const double step_u = cfg.learning_rate_u / bc1, step_t = cfg.learning_rate_theta / bc1;
-            for (int d = tid; d < a.ndof; d += nt) {
-                const double g = gu[d];
-                const double m = sm[a.o_mu + d] + (g - sm[a.o_mu + d]) * (1.0 - b1);
-                const double v = sm[a.o_vu + d] * b2 + (1.0 - b2) * g * g;
-                sm[a.o_mu + d] = m;
-                sm[a.o_vu + d] = v;
-                const double un = u[d] + (-step_u * m) / (sqrt(v) / bc2s + eps);  // addcdiv_: (value*t1)/t2
-                u[d] = a.dof_free[d] ? un : 0.0;
-            }
-            for (int k = 0; k < 2; ++k) {  // density has grad None: Adam skips it
-                const NetDev& n = a.nets[k];
-                if (!n.enabled) continue;
-                for (int i = tid; i < n.d.n_params; i += nt) {
-                    const int p = n.theta_off + i;
-                    const double g = sm[a.o_g + p];
-                    const double m = sm[a.o_m + p] + (g - sm[a.o_m + p]) * (1.0 - b1);
-                    const double v = sm[a.o_v + p] * b2 + (1.0 - b2) * g * g;
-                    sm[a.o_m + p] = m;
-                    sm[a.o_v + p] = v;
-                    th[p] += (-step_t * m) / (sqrt(v) / bc2s + eps);
-                }
+            for (int q = tid; q < n_active_theta + a.ndof; q += nt) {
+                const bool is_u = q >= n_active_theta;
+                const int p = is_u ? q - n_active_theta : q;
+                double* pm = sm + (is_u ? a.o_mu : a.o_m) + p;
+                double* pv = sm + (is_u ? a.o_vu : a.o_v) + p;
+                const double g = is_u ? gu[p] : sm[a.o_g + p];
+                const double m = *pm + (g - *pm) * (1.0 - b1);
+                const double v = *pv * b2 + (1.0 - b2) * g * g;
+                *pm = m;
+                *pv = v;
+                const double upd = (-(is_u ? step_u : step_t) * m) / (sqrt(v) / bc2s + eps);  // addcdiv_: (value*t1)/t2
+                if (is_u)
+                    u[p] = ms.dof_free[p] ? u[p] + upd : 0.0;
+                else
+                    th[p] += upd;
             }
         }
         __syncthreads();
-        // ---- monitoring (solver.py:304-322): ||u_free||, sum of per-tensor parameter norms ----
+        // ---- monitoring (solver.py:304-322): ||u_free||, per-tensor parameter norms; read by thread 0
+        //      at the top of the next iteration ----
         {
             int tix = 0;
             for (int k = 0; k < kMaxNets; ++k) {
@@ -333,58 +467,41 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
                         const int off = n.theta_off + (wb == 0 ? n.d.w_off[l] : n.d.b_off[l]);
                         const int in = l == 0 ? n.d.in_dim : n.d.w;
                         const int cnt = wb == 0 ? (l == n.d.L ? n.d.w : n.d.w * in) : (l == n.d.L ? 1 : n.d.w);
-                        double s = 0.0;
-                        for (int i = lane; i < cnt; i += 32) s += th[off + i] * th[off + i];
-                        s = warp_sum(s);
+                        double s0 = 0.0, s1 = 0.0;
+                        for (int i = lane; i < cnt; i += 64) {
+                            s0 = fma(th[off + i], th[off + i], s0);
+                            if (i + 32 < cnt) s1 = fma(th[off + i + 32], th[off + i + 32], s1);
+                        }
+                        const double s = warp_sum(s0 + s1);
                         if (lane == 0) sm[a.o_tn + tix] = sqrt(s);
                     }
                 }
             }
             if (warp == nwarp - 1) {
                 double s = 0.0;
-                for (int d = lane; d < a.ndof; d += 32) s += a.dof_free[d] ? u[d] * u[d] : 0.0;
+                for (int d = lane; d < a.ndof; d += 32) s += ms.dof_free[d] ? u[d] * u[d] : 0.0;
                 s = warp_sum(s);
                 if (lane == 0) red[4] = sqrt(s);
             }
         }
-        __syncthreads();
-        if (tid == 0) {
-            double tn = 0.0;
-            for (int q = 0; q < a.n_tensors; ++q) tn += sm[a.o_tn + q];
-            if (a.history) {
-                double* h = a.history + (prob * cfg.max_iterations + it) * PF_GD_HISTORY_COLS;
-                h[0] = (double)(it + 1);
-                h[1] = red[2];
-                h[2] = red[0];
-                h[3] = cfg.n_measured > 0 ? red[1] : 0.0;
-                h[4] = red[4];
-                h[5] = red[3];
-                h[6] = tn;
-            }
-            int c = 0;
-            if (it > 10) {  // solver.py:341-355 (legacy nn_solver_gd.py:171: loss only)
-                if (cfg.loss_mode == 0 && red[3] < cfg.tolerance) c = 1;
-                else if (!isnan(red[2]) && red[2] < cfg.tolerance) c = 1;
-            }
-            red[5] = (double)c;
-        }
-        __syncthreads();
-        it_done = it + 1;
-        if (red[5] != 0.0) {
-            conv = 1;
-            break;
-        }
+        __syncthreads();  // norms visible to thread 0, which closes this iteration at the top of the next one
     }
 
     // ---- results: theta, u, reactions f_int - lambda f_ext on fixed DOFs (solver.py:374-380) ----
-    nets_forward(a, sm);
-    gather_linear(a, sm, u, sm + a.o_f);
+    __syncthreads();
+    for (int l = 0; l < maxL; ++l) {
+        forward_hidden(a, sm, l);
+        __syncthreads();
+    }
+    forward_output(a, sm);
+    __syncthreads();
+    gather_linear(a, ms, sm, u, [&](int d, double f) { sm[a.o_f + d] = f; });
     __syncthreads();
     for (int i = tid; i < a.ntheta; i += nt) a.theta[prob * a.ntheta + i] = th[i];
     for (int d = tid; d < a.ndof; d += nt) {
         a.u[prob * a.ndof + d] = u[d];
         if (a.reactions)
-            a.reactions[prob * a.ndof + d] = a.dof_free[d] ? 0.0 : __dsub_rn(sm[a.o_f + d], __dmul_rn(lam, sm[a.o_fext + d]));
+            a.reactions[prob * a.ndof + d] = ms.dof_free[d] ? 0.0 : __dsub_rn(sm[a.o_f + d], __dmul_rn(lam, sm[a.o_fext + d]));
     }
     if (tid == 0) {
         a.n_iters[prob] = it_done;
@@ -469,9 +586,18 @@ extern "C" int pf_gd_solve(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob
     a.o_gf = take(a.ndof);
     a.o_fext = take(a.ndof);
     a.o_gval = take(2 * a.nelem);
-    a.o_delta = take(2 * a.nelem * max_w);
+    a.wmax = max_w;
+    a.o_delta = take(4 * a.nelem * max_w);
     a.o_red = take(8);
     a.o_tn = take(std::max(ntens, 1));
+    a.ninc = (int)plan->ninc;
+    a.o_incgeo = take(4 * a.ninc);
+    a.o_elemgeo = take(4 * a.nelem);
+    a.o_mvals = take(std::max(cfg->n_measured, 1));
+    {
+        const int nints = ((a.nnode + 2) & ~1) + 2 * a.ninc + 2 * a.nelem + 2 * a.ndof + 2 * cfg->n_measured + 2;
+        a.o_ints = take((nints + 1) / 2);
+    }
     for (int k = 0; k < kMaxNets; ++k) {
         NetDev& n = a.nets[k];
         n.val_off = take(2 * a.nelem);
