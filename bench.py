@@ -53,12 +53,13 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.t_mark = 0.0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -66,7 +67,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: samples before it (warm-up) are reported separately."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -77,9 +82,9 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, timed = [], [], set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -88,17 +93,61 @@ class ClockSampler:
                 mx.append(float(parts[1]))
             except ValueError:
                 continue
+            timed += ts >= self.t_mark
             for nm, val in zip(names, parts[2:6]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_in_timed_region": timed, "reasons": sorted(reasons),
+                "window": "warm-up + timed region (nvidia-smi -lms 20)"}
 
 
 def algorithmic_bytes(nelem, nnode, B):
     """per problem 16*nelem (E, A) + 32*nnode (u read, r write); the mesh
     indices/coordinates (8*nelem + 16*nnode) are counted once per sweep."""
     return B * (16 * nelem + 32 * nnode) + 8 * nelem + 16 * nnode
+
+
+def synthetic_inputs(ndof, nelem, B, rank, device):
+    """This rank's shard of the synthetic batch: problems are seeded per rank (1234 + rank), so
+    shards differ between ranks and a rerun reproduces them."""
+    import torch
+
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    u = (torch.rand((ndof, B), generator=g, device=device, dtype=torch.float64) - 0.5) * 2e-3
+    E = torch.rand((nelem, B), generator=g, device=device, dtype=torch.float64) + 0.5
+    A = torch.rand((nelem, B), generator=g, device=device, dtype=torch.float64) + 0.5
+    fx = torch.randn(ndof, generator=g, device=device, dtype=torch.float64) * 1e-3
+    return u, E, A, fx
+
+
+def tangent_algorithmic_bytes(nelem, nnode, nnzb, B):
+    """SURVEY.md 8(d), tangent only: per problem 16*nelem (E, A) + 32*nnzb (2x2 fp64 blocks written);
+    mesh indices/geometry once per sweep: 8*nelem (conn) + 16*nnode (coords) + 16*nelem (block slots)."""
+    return B * (16 * nelem + 32 * nnzb) + 24 * nelem + 16 * nnode
+
+
+def tangent_leg(plan, E, A, dev, Bt, steps, peak):
+    """Secondary line: tangent stiffness K_t into node-block CSR for Bt problems of the shard."""
+    import torch
+
+    Et, At = E[:, :Bt].contiguous(), A[:, :Bt].contiguous()
+    vals = plan.tangent_bsr(Et, At, B=Bt)
+    for _ in range(2):
+        plan.tangent_bsr(Et, At, B=Bt, out=vals)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        plan.tangent_bsr(Et, At, B=Bt, out=vals)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    ab = tangent_algorithmic_bytes(plan.nelem, plan.nnode, plan.nnzb, Bt)
+    return {"problems": Bt, "ms_per_launch": ms, "element_evals_per_s": Bt * plan.nelem / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "kernel": "tangent_bsr_kernel<2,0>", "achieved": ab / (ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": ab / (ms * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes_per_launch": ab}, "gpu_launches": steps + 3}
 
 
 def cpu_reference_leg(steps, warmup, sample_problems=None):
@@ -150,6 +199,7 @@ def main():
     ap.add_argument("--e2e-problems", type=int, default=0, help="problems in the host-buffer leg (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gd", action="store_true")
+    ap.add_argument("--no-tangent", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -188,6 +238,7 @@ def main():
 
     from pinn_fem_b200 import AssemblyPlan
     from pinn_fem_b200.meshes import lattice_truss
+    from pinn_fem_b200.sharding import max_over_ranks
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: pinn_fem_b200 has no CPU fallback")
@@ -199,11 +250,7 @@ def main():
     nodes, el, fixed = lattice_truss(args.nx)
     plan = AssemblyPlan(nodes, el, fixed, device=dev)
     B = args.problems_per_gpu
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    u = (torch.rand((plan.ndof, B), generator=g, device=dev, dtype=torch.float64) - 0.5) * 2e-3
-    E = torch.rand((plan.nelem, B), generator=g, device=dev, dtype=torch.float64) + 0.5
-    A = torch.rand((plan.nelem, B), generator=g, device=dev, dtype=torch.float64) + 0.5
-    fx = torch.randn(plan.ndof, generator=g, device=dev, dtype=torch.float64) * 1e-3
+    u, E, A, fx = synthetic_inputs(plan.ndof, plan.nelem, B, rank, dev)
     r = torch.empty_like(u)
 
     def barrier():
@@ -211,11 +258,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         plan.residual_into(u, E, A, fx, 1.0, r)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -225,10 +273,7 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
-    ms_t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_max = float(ms_t.item())
+    ms_max = max_over_ranks(ms, dev)
     ms_per_step = ms_max / args.steps
     value = world * B * plan.nelem * args.steps / (ms_max * 1e-3)
 
@@ -275,10 +320,7 @@ def main():
         plan.residual_host(uh, Eh, Ah, fxh, 1.0, rh)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * Be * plan.nelem * e2e_steps / float(e2e_t.item())
+    e2e_value = world * Be * plan.nelem * e2e_steps / max_over_ranks(e2e_s, dev)
     e2e_ok = bool(torch.equal(rh[:, :8], r[:, :8].cpu()))
     e2e = {"value": e2e_value, "unit": "element_evals/s",
            "h2d_bytes_per_step": (plan.ndof + 2 * plan.nelem) * Be * 8 + plan.ndof * 8,
@@ -288,6 +330,14 @@ def main():
     launches = args.steps + e2e_steps * ((Be + 127) // 128)
 
     extra = {}
+    if not args.no_tangent:
+        try:
+            extra["tangent_bsr"] = tangent_leg(plan, E, A, dev, min(B, 16), max(3, min(args.steps, 10)), peak)
+            t_ms = max_over_ranks(extra["tangent_bsr"]["ms_per_launch"], dev)
+            extra["tangent_bsr"]["element_evals_per_s"] = world * min(B, 16) * plan.nelem / (t_ms * 1e-3)
+            launches += extra["tangent_bsr"].pop("gpu_launches")
+        except Exception as exc:
+            extra["tangent_bsr"] = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_gd:
         try:
             from pinn_fem_b200.bench_gd import gd_iterations_per_second

@@ -209,8 +209,10 @@ class AssemblyPlan:
                                             _ptr(gE), _ptr(gA), _stream_ptr(self.device)))
         return gE, gA
 
-    def tangent_bsr(self, E, A, u=None, kind="linear", B: Optional[int] = None) -> torch.Tensor:
-        """Node-block CSR values ``[nnzb, dim, dim]`` (or ``[nnzb, dim*dim, B]``)."""
+    def tangent_bsr(self, E, A, u=None, kind="linear", B: Optional[int] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Node-block CSR values ``[nnzb, dim, dim]`` (or ``[nnzb, dim*dim, B]``); ``out`` reuses a
+        buffer of that shape."""
         self._need_device()
         if u is not None:
             B = self._chk(u, self.ndof, "u")
@@ -220,7 +222,13 @@ class AssemblyPlan:
         d = self.dim
         batched = (u is not None and u.dim() == 2) or (u is None and E.dim() == 2)
         shape = (self.nnzb, d * d, B) if batched else (self.nnzb, d, d)
-        vals = torch.empty(shape, dtype=torch.float64, device=self.device)
+        if out is not None:
+            if tuple(out.shape) != shape or out.dtype != torch.float64 or not out.is_contiguous() \
+                    or out.device != self.device:
+                raise ValueError(f"out must be a contiguous float64 tensor of shape {shape} on {self.device}")
+            vals = out
+        else:
+            vals = torch.empty(shape, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             check(self._lib.pf_tangent_bsr(self._handle, KINDS[kind], B, _ptr(u), _ptr(E), _ptr(A), mb, _ptr(vals),
                                            _stream_ptr(self.device)))
