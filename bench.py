@@ -159,7 +159,13 @@ def cpu_reference_leg(steps, warmup, sample_problems=None):
     from oracle import c_oracle
     from oracle import pinnfem_oracle as O
 
-    threads = c_oracle.max_threads()
+    # every host core this process may run on: torchrun exports OMP_NUM_THREADS=1, which is not a
+    # property of the machine, so the thread count is passed to the OpenMP region explicitly
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    threads = max(threads, c_oracle.max_threads())
     nodes, el, fixed = O.lattice_truss(NX)
     Bs = sample_problems or threads * CPU_SAMPLE_PROBLEMS_PER_THREAD
     rng = np.random.default_rng(0)
