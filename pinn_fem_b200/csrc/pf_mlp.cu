@@ -7,6 +7,8 @@
 // and delta passes and a strided set of (out,in) weight pairs in the gradient
 // pass.  All reductions run in a fixed order (ascending point inside a CTA,
 // ascending CTA across the grid) so results are bitwise reproducible.
+#include <cstdlib>
+
 #include "pf_internal.h"
 #include "pf_mlp.cuh"
 
@@ -304,6 +306,24 @@ static int mlp_common(pf_plan* plan, int input_dim, int hidden_layers, int width
 
 constexpr size_t kSmemLimit = 220 * 1024;
 
+// pf_mlp_tc.cu: DMMA kernels for large point sets
+int pf_mlp_tc_grid(const PfMlpDesc& d, bool backward, int64_t n, int sm_count);
+int pf_mlp_tc_launch(const PfMlpDesc& d, bool backward, const double* theta, int64_t n, const double* X,
+                     const double* centroid, double load_factor, double scale, int positive, const double* g_out,
+                     double* out, double* part, int grid, cudaStream_t st);
+constexpr int64_t kTcMinPoints = 2048;  // below this the per-CTA weight staging of the DMMA kernel does not pay
+
+static int sm_count_of(pf_plan* plan) {
+    if (plan) return plan->sm_count;
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+static bool tc_enabled() {
+    static const int off = getenv("PF_MLP_NO_TC") ? atoi(getenv("PF_MLP_NO_TC")) : 0;
+    return !off;
+}
+
 static int pick_pts(const PfMlpDesc& d, bool backward, int* pts, size_t* smem) {
     for (int cand : {128, 64, 32}) {
         const size_t bytes = (size_t)smem_plan(d, backward, cand).total * sizeof(double);
@@ -343,10 +363,19 @@ extern "C" int pf_mlp_forward(pf_plan* plan, int input_dim, int hidden_layers, i
     if (rc) return rc;
     PF_REQUIRE(out != nullptr, "out is NULL");
     if (n == 0) return PF_OK;
+    cudaStream_t st = pf_stream_of(stream);
+    // forward alone is bound by the 2 x w tanh evaluations per point, not by the contractions: the FMA
+    // kernel (no padded columns) is faster there; PF_MLP_FWD_TC=1 selects the DMMA kernel anyway
+    static const int fwd_tc = getenv("PF_MLP_FWD_TC") ? atoi(getenv("PF_MLP_FWD_TC")) : 0;
+    if (fwd_tc && n >= kTcMinPoints && tc_enabled()) {
+        const int grid = pf_mlp_tc_grid(d, false, n, sm_count_of(plan));
+        if (grid > 0)
+            return pf_mlp_tc_launch(d, false, theta, n, X, cen, load_factor, scale, enforce_positive, nullptr, out,
+                                    nullptr, grid, st);
+    }
     int pts;
     size_t smem;
     if ((rc = pick_pts(d, false, &pts, &smem))) return rc;
-    cudaStream_t st = pf_stream_of(stream);
 #define PF_FWD(P)                                                                                             \
     do {                                                                                                      \
         if ((rc = set_smem(mlp_forward_kernel<P>, smem))) return rc;                                          \
@@ -392,6 +421,19 @@ extern "C" int pf_mlp_backward(pf_plan* plan, int input_dim, int hidden_layers, 
     if (n == 0) {
         PF_CUDA_CHECK(cudaMemsetAsync(g_theta, 0, d.n_params * sizeof(double), st));
         return PF_OK;
+    }
+    if (n >= kTcMinPoints && tc_enabled()) {
+        const int grid = pf_mlp_tc_grid(d, true, n, sm_count_of(plan));
+        if (grid > 0) {
+            double* tpart = nullptr;
+            if ((rc = scratch(plan, (size_t)grid * d.n_params * sizeof(double), &tpart))) return rc;
+            rc = pf_mlp_tc_launch(d, true, theta, n, X, cen, load_factor, scale, enforce_positive, g_out, nullptr,
+                                  tpart, grid, st);
+            if (rc) return rc;
+            reduce_rows_kernel<<<(d.n_params + 127) / 128, 128, 0, st>>>(tpart, grid, d.n_params, g_theta);
+            PF_CUDA_CHECK(cudaGetLastError());
+            return PF_OK;
+        }
     }
     int pts;
     size_t smem;

@@ -53,6 +53,30 @@ def test_mlp_forward_backward_jacobian(shape, n):
     assert rel(y0, O.mlp_forward(spec_o, theta, X, 1.0, enforce_positive=False)) < 1e-13
 
 
+@pytest.mark.parametrize("shape", [(3, 2, 20), (3, 2, 15), (3, 2, 16), (2, 1, 7), (3, 4, 33), (5, 3, 64), (3, 3, 8)])
+@pytest.mark.parametrize("n", [2048, 4100, 70000])
+def test_mlp_tensor_core_path(shape, n, monkeypatch):
+    """Large point sets go through the DMMA (fp64 tensor-core) kernels: same parity bar vs the oracle,
+    bitwise reproducible, and consistent with the generic kernels."""
+    from pinn_fem_b200 import ops
+
+    spec_o, spec = O.NetSpec(*shape), ops.NetSpec(*shape)
+    rng = np.random.default_rng(n + shape[2])
+    theta = rng.normal(scale=0.4, size=spec_o.n_params)
+    X = rng.normal(size=(n, shape[0]))
+    g = rng.normal(size=n)
+    y = ops.mlp_forward(spec, dev(theta), dev(X), scale=2.5)
+    assert rel(y, O.mlp_forward(spec_o, theta, X, 2.5)) < 1e-13
+    gt = ops.mlp_backward(spec, dev(theta), dev(g), dev(X), scale=2.5)
+    assert rel(gt, O.mlp_backward(spec_o, theta, X, g, 2.5)) < 1e-11
+    assert torch.equal(gt, ops.mlp_backward(spec, dev(theta), dev(g), dev(X), scale=2.5))
+    y0 = ops.mlp_forward(spec, dev(theta), dev(X), scale=1.0, enforce_positive=False)
+    assert rel(y0, O.mlp_forward(spec_o, theta, X, 1.0, enforce_positive=False)) < 1e-13
+    # the first 1000 points through the generic kernels (below the tensor-core threshold)
+    y_small = ops.mlp_forward(spec, dev(theta), dev(X[:1000]), scale=2.5)
+    assert rel(y[:1000], y_small.cpu().numpy()) < 1e-14
+
+
 def test_mlp_at_plan_centroids_matches_reference_values(golden_dir):
     """NNProperty.value at the example's centroids: inputs are [load_factor, x, y] (D6)."""
     from pinn_fem_b200 import AssemblyPlan, ops
