@@ -350,6 +350,10 @@ def main():
 
             extra["pinn_gd"] = gd_iterations_per_second(dev, world)
             launches += extra["pinn_gd"].get("gpu_launches", 0)
+            from pinn_fem_b200.bench_gd import gd_large_mesh_iterations_per_second
+
+            extra["pinn_gd_large_mesh"] = gd_large_mesh_iterations_per_second(dev, plan, world)
+            launches += extra["pinn_gd_large_mesh"].pop("gpu_launches", 0)
         except Exception as exc:  # the headline metric must not depend on the secondary one
             extra["pinn_gd"] = {"error": f"{type(exc).__name__}: {exc}"}
 

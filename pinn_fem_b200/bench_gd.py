@@ -69,3 +69,41 @@ def gd_iterations_per_second(device, world=1, iters=2000, batched_problems=512, 
                                                            "on the survey container's CPU (indicative)"}
     out["gpu_launches"] = launches
     return out
+
+
+def gd_large_mesh_iterations_per_second(device, plan, world=1, iters=40):
+    """PINN-GD on the C5 lattice itself (one inverse problem per GPU, 999,941 elements): E and A are the
+    521- and 316-parameter MLPs evaluated at every element centroid each iteration, the loop is the
+    device-resident multi-kernel sequence of pf_gd_large.cu (MLP backward on the fp64 tensor pipe)."""
+    nets = [ops.NetSpec(3, 2, 20), ops.NetSpec(3, 2, 15), None]
+    g = torch.Generator(device=device).manual_seed(7)
+    f_ext = torch.randn(plan.ndof, generator=g, device=device, dtype=torch.float64) * 1e-3
+    theta0 = _theta0(1, device)[:, : nets[0].n_params + nets[1].n_params].contiguous()
+    md = np.arange(2 * plan.nnode - 64, 2 * plan.nnode, dtype=np.int64)
+    mv = np.linspace(-1e-3, 1e-3, md.size)
+    kw = dict(max_iterations=iters, tolerance=0.0, learning_rate_u=1e-5, learning_rate_theta=5e-4, alpha_physics=1.0,
+              alpha_data=100.0, load_factor=1.0)
+    best = None
+    for rep in range(2):
+        theta = theta0.clone()
+        u = torch.zeros((1, plan.ndof), dtype=torch.float64, device=device)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = ops.gd_solve(plan, nets, [1.0, 1.0, 1.0], theta, u, f_ext, md, mv, **kw)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    assert int(res.n_iters[0]) == iters
+    t = torch.tensor([best], device=device, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"workload": f"{plan.nelem}-element lattice, one inverse problem per GPU, E and A = MLPs (837 parameters) at "
+                        f"every centroid, 64 measured DOFs, {iters} iterations (tolerance 0), history recorded",
+            "dtype": "f64", "ms_per_iteration": ms / iters, "iters_per_s": world * iters / (ms * 1e-3),
+            "element_evals_per_s": world * iters * plan.nelem / (ms * 1e-3),
+            "gpu_launches": 2 * iters * 12}

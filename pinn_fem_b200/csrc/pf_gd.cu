@@ -11,7 +11,7 @@
 //
 // Everything is fp64 and every reduction runs in a fixed order, so a run is
 // bitwise reproducible.  Meshes/networks that do not fit the shared-memory
-// budget are rejected with PF_ERR_ARG (the host then uses the multi-kernel path).
+// budget run the same iteration as a sequence of kernels (pf_gd_large.cu).
 #include <algorithm>
 
 #include "pf_element.cuh"
@@ -605,8 +605,9 @@ extern "C" int pf_gd_solve(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob
     }
     a.smem_doubles = off;
     const size_t smem = (size_t)off * sizeof(double);
-    PF_REQUIRE(smem <= 200 * 1024,
-               "problem too large for the single-CTA gradient-descent kernel (%zu bytes of shared memory needed)", smem);
+    if (smem > 200 * 1024)  // does not fit one CTA: the multi-kernel device-resident loop (pf_gd_large.cu)
+        return pf_gd_solve_large(plan, cfg, nprob, theta, u, f_ext, meas_dofs, meas_vals, history, n_iters, converged,
+                                 reactions, pf_stream_of(stream));
     if (smem > 48 * 1024)
         PF_CUDA_CHECK(cudaFuncSetAttribute(gd_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int work = std::max({a.nelem * max_w, a.ndof, max_w * max_w + max_w, 32});

@@ -1,0 +1,366 @@
+// Device-resident PINN gradient descent for meshes that do not fit one CTA's shared memory
+// (fem/solver.py:252-355 on ~10^6 elements).
+//
+// One iteration is a fixed sequence of launches on the caller's stream -- material networks at the
+// centroids (pf_mlp_forward), residual + 0.5*sum r^2 (pf_residual, patch/node gather), dL/du = K r
+// (pf_tangent_matvec), dL/dE, dL/dA (pf_material_vjp), dL/dtheta (pf_mlp_backward: DMMA), two Adam
+// updates with BC zeroing, monitoring norms, history row and convergence test -- with every scalar
+// (losses, norms, the converged flag, beta^t) living in device memory.  The host only enqueues; it
+// looks at the converged flag every kPoll iterations.  After convergence the remaining enqueued
+// iterations are no-ops for the state (the update kernels test the flag).
+#include <algorithm>
+#include <vector>
+
+#include "pf_internal.h"
+#include "pf_mlp.cuh"
+
+namespace {
+
+constexpr int kPoll = 8;
+constexpr int kRedThreads = 256;
+
+// device scalars
+enum { S_HALF_SQ = 0, S_DATA_SQ, S_UNORM_SQ, S_POW_B1, S_POW_B2, S_DONE, S_ITERS, S_CONV, S_TN, S_COUNT };
+
+struct LargeCfg {
+    double tolerance, lr_u, lr_t, alpha_p, alpha_d, load_factor, gscale, cdata;
+    int legacy, has_meas, n_meas, nfree, max_iterations;
+};
+
+// sum_j (m_j - u[dof_j])^2 in a fixed order (one block)
+__global__ void __launch_bounds__(kRedThreads) data_loss_kernel(const int32_t* __restrict__ md,
+                                                                const double* __restrict__ mv, int n_meas,
+                                                                const double* __restrict__ u, double* __restrict__ sc) {
+    __shared__ double red[kRedThreads];
+    double s = 0.0;
+    for (int j = threadIdx.x; j < n_meas; j += kRedThreads) {
+        const double d = mv[j] - u[md[j]];
+        s += d * d;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sc[S_DATA_SQ] = red[0];
+}
+
+// Adam on u (torch defaults), data-loss gradient, BC zeroing (solver.py:292-298), partial ||u_free||^2
+__global__ void __launch_bounds__(kRedThreads) adam_u_kernel(LargeCfg c, int64_t ndof, const double* __restrict__ gu,
+                                                             const double* __restrict__ msum,
+                                                             const double* __restrict__ mcnt,
+                                                             const uint8_t* __restrict__ dof_free,
+                                                             double* __restrict__ u, double* __restrict__ m,
+                                                             double* __restrict__ v, const double* __restrict__ sc,
+                                                             double* __restrict__ part) {
+    __shared__ double red[kRedThreads];
+    const bool done = sc[S_DONE] != 0.0;
+    const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    const double pb1 = sc[S_POW_B1] * b1, pb2 = sc[S_POW_B2] * b2;  // beta^t of this iteration
+    const double bc1 = 1.0 - pb1, bc2s = sqrt(1.0 - pb2);
+    const double step = c.lr_u / bc1;
+    double s = 0.0;
+    for (int64_t d = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; d < ndof; d += (int64_t)gridDim.x * kRedThreads) {
+        double ud = u[d];
+        if (!done) {
+            double g = c.gscale * gu[d];
+            if (c.has_meas && mcnt[d] != 0.0) g += c.cdata * (msum[d] - mcnt[d] * ud);
+            const double mm = m[d] + (g - m[d]) * (1.0 - b1);
+            const double vv = v[d] * b2 + (1.0 - b2) * g * g;
+            m[d] = mm;
+            v[d] = vv;
+            ud = dof_free[d] ? ud + (-step * mm) / (sqrt(vv) / bc2s + eps) : 0.0;
+            u[d] = ud;
+        }
+        if (dof_free[d]) s += ud * ud;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+struct TensorList {
+    int n;
+    int off[3 * 2 * (PF_MLP_MAX_LAYERS + 1)];
+    int cnt[3 * 2 * (PF_MLP_MAX_LAYERS + 1)];
+};
+
+// One block: Adam on the active parameters, per-tensor norms, u-norm second stage, history row,
+// convergence test (solver.py:308-355), iteration bookkeeping.
+__global__ void __launch_bounds__(1024) adam_theta_finish_kernel(LargeCfg c, int n_active, int n_theta, TensorList tl,
+                                                                 const double* __restrict__ g, double* __restrict__ theta,
+                                                                 double* __restrict__ m, double* __restrict__ v,
+                                                                 const double* __restrict__ upart, int n_upart,
+                                                                 double* __restrict__ sc, double* __restrict__ history) {
+    __shared__ double tn[3 * 2 * (PF_MLP_MAX_LAYERS + 1)];
+    const bool done = sc[S_DONE] != 0.0;
+    const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    const double pb1 = sc[S_POW_B1] * b1, pb2 = sc[S_POW_B2] * b2;
+    const double bc1 = 1.0 - pb1, bc2s = sqrt(1.0 - pb2);
+    const double step = c.lr_t / bc1;
+    if (!done) {
+        for (int q = threadIdx.x; q < n_active; q += blockDim.x) {
+            const double gq = c.gscale * g[q];
+            const double mm = m[q] + (gq - m[q]) * (1.0 - b1);
+            const double vv = v[q] * b2 + (1.0 - b2) * gq * gq;
+            m[q] = mm;
+            v[q] = vv;
+            theta[q] += (-step * mm) / (sqrt(vv) / bc2s + eps);
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int t = warp; t < tl.n; t += nwarp) {
+        double s = 0.0;
+        for (int i = lane; i < tl.cnt[t]; i += 32) s = fma(theta[tl.off[t] + i], theta[tl.off[t] + i], s);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) tn[t] = sqrt(s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && !done) {
+        double tsum = 0.0;
+        for (int t = 0; t < tl.n; ++t) tsum += tn[t];
+        double un = 0.0;
+        for (int b = 0; b < n_upart; ++b) un += upart[b];
+        const int it = (int)sc[S_ITERS];  // 0-based index of this iteration
+        const double s2 = 2.0 * sc[S_HALF_SQ];
+        const double loss_p = c.legacy ? s2 / (double)c.nfree : 0.5 * s2;
+        const double loss_d = c.has_meas ? sc[S_DATA_SQ] / c.n_meas : 0.0;
+        const double loss = c.alpha_p * loss_p + (c.has_meas ? c.alpha_d * loss_d : 0.0);
+        const double rn = sqrt(s2);
+        if (history) {
+            double* h = history + (int64_t)it * PF_GD_HISTORY_COLS;
+            h[0] = (double)(it + 1);
+            h[1] = loss;
+            h[2] = loss_p;
+            h[3] = c.n_meas > 0 ? loss_d : 0.0;
+            h[4] = sqrt(un);
+            h[5] = rn;
+            h[6] = tsum;
+        }
+        sc[S_POW_B1] = pb1;
+        sc[S_POW_B2] = pb2;
+        sc[S_ITERS] = (double)(it + 1);
+        int conv = 0;
+        if (it > 10) {  // solver.py:341-355 (legacy nn_solver_gd.py:171: loss only)
+            if (!c.legacy && rn < c.tolerance) conv = 1;
+            else if (!isnan(loss) && loss < c.tolerance) conv = 1;
+        }
+        if (conv) {
+            sc[S_CONV] = 1.0;
+            sc[S_DONE] = 1.0;
+        } else if (it + 1 >= c.max_iterations) {
+            sc[S_DONE] = 1.0;
+        }
+    }
+}
+
+__global__ void fill_kernel(double* __restrict__ x, int64_t n, double v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+
+// reactions = f_int - lambda f_ext on fixed DOFs, 0 on free DOFs (solver.py:374-380)
+__global__ void reactions_kernel(const double* __restrict__ f, const double* __restrict__ fext, double lam,
+                                 const uint8_t* __restrict__ dof_free, int64_t ndof, double* __restrict__ out) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < ndof) out[d] = dof_free[d] ? 0.0 : __dsub_rn(f[d], __dmul_rn(lam, fext[d]));
+}
+
+struct DevBuf {
+    std::vector<void*> ptrs;
+    ~DevBuf() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    int alloc(T** out, size_t count) {
+        void* p = nullptr;
+        PF_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+        ptrs.push_back(p);
+        *out = static_cast<T*>(p);
+        return PF_OK;
+    }
+};
+
+}  // namespace
+
+// One problem at a time; called by pf_gd_solve when the single-CTA kernel does not fit.
+int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, double* theta_all, double* u_all,
+                      const double* f_ext, const int32_t* meas_dofs, const double* meas_vals_all, double* history_all,
+                      int32_t* n_iters, int32_t* converged, double* reactions_all, cudaStream_t st) {
+    const int64_t ndof = plan->ndof, nelem = plan->nelem;
+    PfMlpDesc desc[3];
+    int theta_off[3] = {0, 0, 0}, ntheta = 0;
+    TensorList tl{};
+    for (int k = 0; k < 3; ++k) {
+        theta_off[k] = ntheta;
+        if (!cfg->net_enabled[k]) continue;
+        int rc = pf_mlp_make_desc(cfg->net_input_dim[k], cfg->net_hidden_layers[k], cfg->net_width[k], &desc[k]);
+        if (rc) return rc;
+        PF_REQUIRE(desc[k].in_dim == plan->dim + 1,
+                   "network input_dim %d does not match [load_factor, centroid] = %d inputs (fem/properties.py:116-125)",
+                   desc[k].in_dim, plan->dim + 1);
+        for (int l = 0; l <= desc[k].L; ++l) {
+            const int in = l == 0 ? desc[k].in_dim : desc[k].w;
+            tl.off[tl.n] = ntheta + desc[k].w_off[l];
+            tl.cnt[tl.n++] = l == desc[k].L ? desc[k].w : desc[k].w * in;
+            tl.off[tl.n] = ntheta + desc[k].b_off[l];
+            tl.cnt[tl.n++] = l == desc[k].L ? 1 : desc[k].w;
+        }
+        ntheta += desc[k].n_params;
+    }
+    // density never enters the physics: its gradient is None in the reference and Adam skips it
+    const int n_active = cfg->net_enabled[2] ? theta_off[2] : ntheta;
+    const int n_meas = cfg->n_measured;
+    const bool has_meas = n_meas > 0 && meas_dofs && meas_vals_all && cfg->alpha_data > 0.0;
+
+    LargeCfg c{};
+    c.tolerance = cfg->tolerance;
+    c.lr_u = cfg->learning_rate_u;
+    c.lr_t = cfg->learning_rate_theta;
+    c.alpha_p = cfg->alpha_physics;
+    c.alpha_d = cfg->alpha_data;
+    c.load_factor = cfg->load_factor;
+    c.legacy = cfg->loss_mode == 1;
+    c.gscale = c.legacy ? 2.0 * cfg->alpha_physics / (double)plan->nfree : cfg->alpha_physics;
+    c.has_meas = has_meas ? 1 : 0;
+    c.n_meas = n_meas;
+    c.cdata = has_meas ? -2.0 * cfg->alpha_data / n_meas : 0.0;
+    c.nfree = (int)plan->nfree;
+    c.max_iterations = cfg->max_iterations;
+
+    DevBuf buf;
+    double *E, *A, *r, *gu, *gE, *gA, *mu, *vu, *mt, *vt, *gt, *sc, *upart, *msum = nullptr, *mcnt = nullptr, *fint;
+    int rc;
+    if ((rc = buf.alloc(&E, nelem)) || (rc = buf.alloc(&A, nelem)) || (rc = buf.alloc(&r, ndof)) ||
+        (rc = buf.alloc(&gu, ndof)) || (rc = buf.alloc(&gE, nelem)) || (rc = buf.alloc(&gA, nelem)) ||
+        (rc = buf.alloc(&mu, ndof)) || (rc = buf.alloc(&vu, ndof)) || (rc = buf.alloc(&mt, ntheta)) ||
+        (rc = buf.alloc(&vt, ntheta)) || (rc = buf.alloc(&gt, ntheta)) || (rc = buf.alloc(&sc, S_COUNT)) ||
+        (rc = buf.alloc(&fint, ndof)))
+        return rc;
+    const int ublocks = (int)std::min<int64_t>((ndof + kRedThreads - 1) / kRedThreads, 1024);
+    if ((rc = buf.alloc(&upart, ublocks))) return rc;
+    if (has_meas && ((rc = buf.alloc(&msum, ndof)) || (rc = buf.alloc(&mcnt, ndof)))) return rc;
+    // size the plan workspace once (residual partial sums, MLP gradient partials) so it is never
+    // reallocated while iterations are in flight
+    {
+        size_t need = (size_t)std::max<int64_t>(plan->nnode, (int64_t)plan->patches.size()) * sizeof(double);
+        for (int k = 0; k < 2; ++k) {
+            if (!cfg->net_enabled[k]) continue;
+            const size_t rows = nelem >= 2048 ? (size_t)plan->sm_count * 8 : (size_t)((nelem + 31) / 32);
+            need = std::max(need, rows * desc[k].n_params * sizeof(double));
+        }
+        if ((rc = pf_plan_reserve_work(plan, need))) return rc;
+    }
+
+    std::vector<int32_t> h_md;
+    std::vector<double> h_mv, h_sum, h_cnt;
+    if (has_meas) {
+        h_md.resize(n_meas);
+        PF_CUDA_CHECK(cudaMemcpyAsync(h_md.data(), meas_dofs, n_meas * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PF_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int j = 0; j < n_meas; ++j)
+            PF_REQUIRE(h_md[j] >= 0 && h_md[j] < ndof, "measured DOF %d out of range", h_md[j]);
+    }
+    const unsigned eb = (unsigned)((nelem + 255) / 256), db = (unsigned)((ndof + 255) / 256);
+    double h_sc[S_COUNT];
+
+    for (int64_t p = 0; p < nprob; ++p) {
+        double* theta = theta_all ? theta_all + p * ntheta : nullptr;
+        double* u = u_all + p * ndof;
+        const double* mv = has_meas ? meas_vals_all + p * n_meas : nullptr;
+        double* history = history_all ? history_all + p * (int64_t)std::max(cfg->max_iterations, 1) * PF_GD_HISTORY_COLS
+                                      : nullptr;
+        if (has_meas) {  // per-DOF sums of the targets: d/du of mean((m - u)^2) in closed form
+            h_mv.resize(n_meas);
+            PF_CUDA_CHECK(cudaMemcpyAsync(h_mv.data(), mv, n_meas * sizeof(double), cudaMemcpyDeviceToHost, st));
+            PF_CUDA_CHECK(cudaStreamSynchronize(st));
+            h_sum.assign(ndof, 0.0);
+            h_cnt.assign(ndof, 0.0);
+            for (int j = 0; j < n_meas; ++j) {
+                h_sum[h_md[j]] += h_mv[j];
+                h_cnt[h_md[j]] += 1.0;
+            }
+            PF_CUDA_CHECK(cudaMemcpyAsync(msum, h_sum.data(), ndof * sizeof(double), cudaMemcpyHostToDevice, st));
+            PF_CUDA_CHECK(cudaMemcpyAsync(mcnt, h_cnt.data(), ndof * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        PF_CUDA_CHECK(cudaMemsetAsync(mu, 0, ndof * sizeof(double), st));
+        PF_CUDA_CHECK(cudaMemsetAsync(vu, 0, ndof * sizeof(double), st));
+        if (ntheta) {
+            PF_CUDA_CHECK(cudaMemsetAsync(mt, 0, ntheta * sizeof(double), st));
+            PF_CUDA_CHECK(cudaMemsetAsync(vt, 0, ntheta * sizeof(double), st));
+            PF_CUDA_CHECK(cudaMemsetAsync(gt, 0, ntheta * sizeof(double), st));
+        }
+        for (int i = 0; i < S_COUNT; ++i) h_sc[i] = 0.0;
+        h_sc[S_POW_B1] = h_sc[S_POW_B2] = 1.0;
+        if (cfg->max_iterations == 0) h_sc[S_DONE] = 1.0;
+        PF_CUDA_CHECK(cudaMemcpyAsync(sc, h_sc, sizeof(h_sc), cudaMemcpyHostToDevice, st));
+        PF_CUDA_CHECK(cudaStreamSynchronize(st));  // h_sum / h_cnt / h_sc are reused by the next problem
+
+        auto materials = [&]() -> int {
+            for (int k = 0; k < 2; ++k) {
+                double* dst = k == 0 ? E : A;
+                if (cfg->net_enabled[k]) {
+                    int e = pf_mlp_forward(plan, desc[k].in_dim, desc[k].L, desc[k].w, theta + theta_off[k], nelem, nullptr,
+                                           cfg->load_factor, cfg->net_scale[k], 1, dst, st);
+                    if (e) return e;
+                } else {
+                    fill_kernel<<<eb, 256, 0, st>>>(dst, nelem, cfg->net_scale[k]);
+                }
+            }
+            return PF_OK;
+        };
+
+        bool finished = cfg->max_iterations == 0;
+        for (int it = 0; it < cfg->max_iterations && !finished; ++it) {
+            if ((rc = materials())) return rc;
+            // r = f_int - lambda f_ext on free DOFs, 0.5 sum r^2 (solver.py:262-270)
+            if ((rc = pf_residual(plan, PF_ELEM_LINEAR, 1, u, E, A, 0, nullptr, f_ext, 0, cfg->load_factor, r,
+                                  sc + S_HALF_SQ, nullptr, st)))
+                return rc;
+            // reverse pass: dL/du = gscale K r, dL/dE, dL/dA, dL/dtheta (closed form of the autograd graph)
+            if ((rc = pf_tangent_matvec(plan, PF_ELEM_LINEAR, 1, nullptr, E, A, 0, r, gu, st))) return rc;
+            if (n_active) {
+                if ((rc = pf_material_vjp(plan, PF_ELEM_LINEAR, 1, u, E, A, 0, r, gE, gA, st))) return rc;
+                for (int k = 0; k < 2; ++k)
+                    if (cfg->net_enabled[k] &&
+                        (rc = pf_mlp_backward(plan, desc[k].in_dim, desc[k].L, desc[k].w, theta + theta_off[k], nelem,
+                                              nullptr, cfg->load_factor, cfg->net_scale[k], 1, k == 0 ? gE : gA,
+                                              gt + theta_off[k], st)))
+                        return rc;
+            }
+            if (has_meas) data_loss_kernel<<<1, kRedThreads, 0, st>>>(meas_dofs, mv, n_meas, u, sc);
+            adam_u_kernel<<<ublocks, kRedThreads, 0, st>>>(c, ndof, gu, msum, mcnt, plan->d_dof_free, u, mu, vu, sc, upart);
+            adam_theta_finish_kernel<<<1, 1024, 0, st>>>(c, n_active, ntheta, tl, gt, theta, mt, vt, upart, ublocks, sc,
+                                                        history);
+            PF_CUDA_CHECK(cudaGetLastError());
+            if ((it + 1) % kPoll == 0 || it + 1 == cfg->max_iterations) {
+                PF_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+                PF_CUDA_CHECK(cudaStreamSynchronize(st));
+                finished = h_sc[S_DONE] != 0.0;
+            }
+        }
+        if (cfg->max_iterations == 0) {
+            PF_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+            PF_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+        const int32_t iters = (int32_t)h_sc[S_ITERS], conv = (int32_t)h_sc[S_CONV];
+        PF_CUDA_CHECK(cudaMemcpyAsync(n_iters + p, &iters, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        PF_CUDA_CHECK(cudaMemcpyAsync(converged + p, &conv, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if (reactions_all) {
+            if ((rc = materials())) return rc;
+            if ((rc = pf_residual(plan, PF_ELEM_LINEAR, 1, u, E, A, 0, fint, nullptr, 0, 0.0, nullptr, nullptr, nullptr, st)))
+                return rc;
+            reactions_kernel<<<db, 256, 0, st>>>(fint, f_ext, cfg->load_factor, plan->d_dof_free, ndof,
+                                                 reactions_all + p * ndof);
+            PF_CUDA_CHECK(cudaGetLastError());
+        }
+        PF_CUDA_CHECK(cudaStreamSynchronize(st));  // iters / conv are stack variables
+    }
+    return PF_OK;
+}

@@ -366,7 +366,8 @@ extern "C" int pf_mlp_forward(pf_plan* plan, int input_dim, int hidden_layers, i
     cudaStream_t st = pf_stream_of(stream);
     // forward alone is bound by the 2 x w tanh evaluations per point, not by the contractions: the FMA
     // kernel (no padded columns) is faster there; PF_MLP_FWD_TC=1 selects the DMMA kernel anyway
-    static const int fwd_tc = getenv("PF_MLP_FWD_TC") ? atoi(getenv("PF_MLP_FWD_TC")) : 0;
+    const char* fwd_env = getenv("PF_MLP_FWD_TC");  // read per call: the tests flip it
+    const int fwd_tc = fwd_env ? atoi(fwd_env) : 0;
     if (fwd_tc && n >= kTcMinPoints && tc_enabled()) {
         const int grid = pf_mlp_tc_grid(d, false, n, sm_count_of(plan));
         if (grid > 0)

@@ -62,87 +62,6 @@ def _nn_parameter_dict(model):
 # ---------------------------------------------------------------------------------------
 
 
-def _gd_multikernel(plan, slots, scales, theta, u, f_ext, md, mv, *, max_iterations, tolerance, learning_rate_u,
-                    learning_rate_theta, alpha_physics, alpha_data, load_factor, legacy_loss):
-    """Same iteration as the single-CTA kernel, one launch per stage, for meshes that do not fit
-    one CTA's shared memory (fem/solver.py:252-355)."""
-    dev = plan.device
-    free = torch.as_tensor(plan.free_dofs.copy(), device=dev)
-    fixed = torch.as_tensor(plan.fixed_dofs.copy(), device=dev)
-    specs = [s for _, s in slots]
-    offs, off = [], 0
-    for s in specs:
-        offs.append(off)
-        off += s.spec.n_params if s is not None else 0
-    has_meas = md is not None and alpha_data > 0
-    m_u, v_u = torch.zeros_like(u), torch.zeros_like(u)
-    m_t, v_t = torch.zeros_like(theta), torch.zeros_like(theta)
-    history, converged = [], False
-    b1, b2, eps = 0.9, 0.999, 1e-8
-
-    def field_of(k):
-        s = specs[k]
-        if s is None:
-            return torch.full((plan.nelem,), scales[k], dtype=torch.float64, device=dev)
-        return ops.mlp_forward(s.spec, theta[offs[k]:offs[k] + s.spec.n_params].contiguous(), plan=plan,
-                               load_factor=load_factor, scale=s.scale, enforce_positive=s.enforce_positive)
-
-    for it in range(int(max_iterations)):
-        E, A = field_of(0), field_of(1)
-        out = plan.residual(u, E, A, f_ext, load_factor, f_int=False, r=True)
-        r = out["r"]
-        s2 = float(torch.sum(r * r))
-        loss_p = s2 / plan.nfree if legacy_loss else 0.5 * s2
-        gscale = (2.0 * alpha_physics / plan.nfree) if legacy_loss else alpha_physics
-        gf = gscale * r
-        g_u = plan.tangent_matvec(gf, E, A)
-        loss_d = 0.0
-        if has_meas:
-            rd = mv - u[md]
-            loss_d = float(torch.mean(rd * rd))
-            g_u.index_add_(0, md, (-2.0 * alpha_data / md.numel()) * rd)
-        loss = alpha_physics * loss_p + (alpha_data * loss_d if has_meas else 0.0)
-        gE, gA = plan.material_vjp(u, E, A, gf)
-        g_t = torch.zeros_like(theta)
-        for k, gval in ((0, gE), (1, gA)):
-            s = specs[k]
-            if s is not None:
-                n = s.spec.n_params
-                g_t[offs[k]:offs[k] + n] = ops.mlp_backward(s.spec, theta[offs[k]:offs[k] + n].contiguous(), gval,
-                                                            plan=plan, load_factor=load_factor, scale=s.scale,
-                                                            enforce_positive=s.enforce_positive)
-        t = it + 1
-        bc1, bc2s = 1.0 - b1 ** t, (1.0 - b2 ** t) ** 0.5
-        m_u += (g_u - m_u) * (1.0 - b1)
-        v_u.mul_(b2).addcmul_(g_u, g_u, value=1.0 - b2)
-        u.addcdiv_(m_u, v_u.sqrt() / bc2s + eps, value=-learning_rate_u / bc1)
-        u[fixed] = 0.0
-        active = offs[2] if specs[2] is not None else theta.numel()  # density parameters are never updated
-        if active:
-            m_t[:active] += (g_t[:active] - m_t[:active]) * (1.0 - b1)
-            v_t[:active].mul_(b2).addcmul_(g_t[:active], g_t[:active], value=1.0 - b2)
-            theta[:active].addcdiv_(m_t[:active], v_t[:active].sqrt() / bc2s + eps, value=-learning_rate_theta / bc1)
-        tn = 0.0
-        for k, s in enumerate(specs):
-            if s is None:
-                continue
-            o = offs[k]
-            for p in s.net.parameters():
-                tn += float(torch.linalg.vector_norm(theta[o:o + p.numel()]))
-                o += p.numel()
-        res_norm = s2 ** 0.5
-        history.append([float(t), loss, loss_p, loss_d if md is not None else 0.0,
-                        float(torch.linalg.vector_norm(u[free])), res_norm, tn])
-        if it > 10:
-            if (not legacy_loss and res_norm < tolerance) or (not np.isnan(loss) and loss < tolerance):
-                converged = True
-                break
-    E, A = field_of(0), field_of(1)
-    reac = plan.residual(u, E, A)["f_int"] - load_factor * f_ext
-    reac[free] = 0.0
-    return np.array(history).reshape(-1, 7), converged, reac
-
-
 def _run_gd(model, loads, measured_disp, measured_dofs, u_initial, *, max_iterations, tolerance, learning_rate_u,
             learning_rate_theta, alpha_physics, alpha_data, load_factor, legacy_loss=False):
     """One ``solve_gd`` inner loop on the device; mutates the model's networks like the reference."""
@@ -165,20 +84,14 @@ def _run_gd(model, loads, measured_disp, measured_dofs, u_initial, *, max_iterat
     kw = dict(max_iterations=int(max_iterations), tolerance=float(tolerance), learning_rate_u=learning_rate_u,
               learning_rate_theta=learning_rate_theta, alpha_physics=alpha_physics, alpha_data=alpha_data,
               load_factor=float(load_factor), legacy_loss=legacy_loss)
-    try:
-        res = ops.gd_solve(plan, nets, scales, theta if theta.numel() else None, u, f_ext, md, mv, **kw)
-        n = int(res.n_iters[0])
-        H = res.history[0, :n].cpu().numpy()
-        converged = bool(res.converged[0])
-        reactions = res.reactions[0]
-        theta_out, u_out = res.theta[0], res.u[0]
-    except ValueError as exc:
-        if "too large for the single-CTA" not in str(exc):
-            raise
-        mdt = torch.as_tensor(md, device=dev) if has_meas else None
-        mvt = to_dev(mv, dev) if has_meas else None
-        u_out, theta_out = u[0].clone(), theta[0].clone()
-        H, converged, reactions = _gd_multikernel(plan, slots, scales, theta_out, u_out, f_ext, mdt, mvt, **kw)
+    # one device-resident loop: a single CTA per problem when the mesh fits in shared memory, else the
+    # multi-kernel loop of pf_gd_large.cu -- chosen inside pf_gd_solve
+    res = ops.gd_solve(plan, nets, scales, theta if theta.numel() else None, u, f_ext, md, mv, **kw)
+    n = int(res.n_iters[0])
+    H = res.history[0, :n].cpu().numpy()
+    converged = bool(res.converged[0])
+    reactions = res.reactions[0]
+    theta_out, u_out = res.theta[0], res.u[0]
     if theta_out.numel():
         unpack_theta(model, theta_out)
     has_nn = any(p is not None for _, p in slots)

@@ -65,6 +65,7 @@ def test_mlp_tensor_core_path(shape, n, monkeypatch):
     theta = rng.normal(scale=0.4, size=spec_o.n_params)
     X = rng.normal(size=(n, shape[0]))
     g = rng.normal(size=n)
+    monkeypatch.setenv("PF_MLP_FWD_TC", "1")  # forward defaults to the FMA kernel (tanh bound); test the DMMA one
     y = ops.mlp_forward(spec, dev(theta), dev(X), scale=2.5)
     assert rel(y, O.mlp_forward(spec_o, theta, X, 2.5)) < 1e-13
     gt = ops.mlp_backward(spec, dev(theta), dev(g), dev(X), scale=2.5)
@@ -72,9 +73,10 @@ def test_mlp_tensor_core_path(shape, n, monkeypatch):
     assert torch.equal(gt, ops.mlp_backward(spec, dev(theta), dev(g), dev(X), scale=2.5))
     y0 = ops.mlp_forward(spec, dev(theta), dev(X), scale=1.0, enforce_positive=False)
     assert rel(y0, O.mlp_forward(spec_o, theta, X, 1.0, enforce_positive=False)) < 1e-13
-    # the first 1000 points through the generic kernels (below the tensor-core threshold)
-    y_small = ops.mlp_forward(spec, dev(theta), dev(X[:1000]), scale=2.5)
-    assert rel(y[:1000], y_small.cpu().numpy()) < 1e-14
+    # the same points through the FMA kernel
+    monkeypatch.setenv("PF_MLP_FWD_TC", "0")
+    y_fma = ops.mlp_forward(spec, dev(theta), dev(X), scale=2.5)
+    assert rel(y, y_fma.cpu().numpy()) < 1e-14
 
 
 def test_mlp_at_plan_centroids_matches_reference_values(golden_dir):
@@ -240,3 +242,55 @@ def test_gd_on_a_larger_mesh_vs_oracle():
     assert rel(res.u[0], u_ref) < 1e-9 and rel(res.reactions[0], reac_ref) < 1e-8
     assert rel(res.theta[0], np.concatenate([mat.young[1], mat.area[1]])) < 1e-9
     assert rel(res.history[0, :25, 1], np.array([h["loss_total"] for h in hist])) < 1e-9
+
+
+@pytest.mark.parametrize("case", ["nets", "scalar_area", "converges"])
+def test_gd_large_mesh_device_loop_vs_oracle(case):
+    """Meshes that do not fit one CTA's shared memory run the same iteration as a device-resident
+    sequence of kernels (pf_gd_large.cu): 40x40 lattice (4641 elements, MLP backward on DMMA), duplicate
+    measured DOFs, parity with the oracle's solve_gd iteration by iteration."""
+    from pinn_fem_b200 import AssemblyPlan, ops
+
+    nodes, el, fixed = O.lattice_truss(40)
+    rng = np.random.default_rng(21)
+    loads = np.zeros(2 * len(nodes))
+    loads[-2], loads[-1] = 0.05, -0.02
+    mesh = O.Mesh(nodes, el, loads, fixed)
+    specs = (O.NetSpec(3, 2, 20), O.NetSpec(3, 2, 15))
+    th = [rng.normal(scale=0.3, size=s.n_params) for s in specs]
+    md = np.array([2 * 799, 2 * 799 + 1, 411, 411, 1202])
+    mv = np.array([0.01, -0.02, 0.005, 0.004, -0.003])
+    n_it, tol = 20, 1e-14
+    if case == "nets":
+        mat = O.MaterialNets((specs[0], th[0].copy(), 2.0), (specs[1], th[1].copy(), 1.5), 1.0)
+        nets, scales, theta0 = [ops.NetSpec(3, 2, 20), ops.NetSpec(3, 2, 15), None], [2.0, 1.5, 1.0], np.concatenate(th)
+    elif case == "scalar_area":
+        mat = O.MaterialNets((specs[0], th[0].copy(), 2.0), 1.5, 1.0)
+        nets, scales, theta0 = [ops.NetSpec(3, 2, 20), None, None], [2.0, 1.5, 1.0], th[0]
+    else:  # loose tolerance: stops on the loss test right after iteration 11 (checked only for it > 10)
+        mat = O.MaterialNets((specs[0], th[0].copy(), 2.0), (specs[1], th[1].copy(), 1.5), 1.0)
+        nets, scales, theta0 = [ops.NetSpec(3, 2, 20), ops.NetSpec(3, 2, 15), None], [2.0, 1.5, 1.0], np.concatenate(th)
+        n_it, tol = 40, 1e3
+    u_ref, reac_ref, ok, hist = O.solve_gd(mesh, mat, n_it, tol, lr_u=1e-4, lr_theta=1e-3, alpha_d=10.0,
+                                           meas_dofs=md, meas_vals=mv, lam=0.9)
+    plan = AssemblyPlan(nodes, el, fixed, device="cuda")
+    theta = dev(theta0)[None].clone()
+    res = ops.gd_solve(plan, nets, scales, theta, torch.zeros((1, plan.ndof), dtype=torch.float64, device="cuda"),
+                       dev(loads), md, mv, max_iterations=n_it, tolerance=tol, learning_rate_u=1e-4,
+                       learning_rate_theta=1e-3, alpha_data=10.0, load_factor=0.9)
+    n = int(res.n_iters[0])
+    assert n == len(hist) and bool(res.converged[0]) == bool(ok)
+    if case == "converges":
+        assert n == 12 and ok
+    assert rel(res.u[0], u_ref) < 1e-9 and rel(res.reactions[0], reac_ref) < 1e-8
+    th_ref = np.concatenate([mat.young[1], mat.area[1]]) if case != "scalar_area" else mat.young[1]
+    assert rel(res.theta[0], th_ref) < 1e-9
+    for col, key in ((1, "loss_total"), (2, "loss_physics"), (3, "loss_data"), (4, "u_norm"), (5, "residual_norm"),
+                     (6, "theta_norm")):
+        assert rel(res.history[0, :n, col], np.array([h[key] for h in hist])) < 1e-9, key
+    # bitwise reproducible
+    theta2 = dev(theta0)[None].clone()
+    res2 = ops.gd_solve(plan, nets, scales, theta2, torch.zeros((1, plan.ndof), dtype=torch.float64, device="cuda"),
+                        dev(loads), md, mv, max_iterations=n_it, tolerance=tol, learning_rate_u=1e-4,
+                        learning_rate_theta=1e-3, alpha_data=10.0, load_factor=0.9)
+    assert torch.equal(res.u, res2.u) and torch.equal(res.theta, res2.theta)
