@@ -150,6 +150,31 @@ def tangent_leg(plan, E, A, dev, Bt, steps, peak):
                          "algorithmic_bytes_per_launch": ab}, "gpu_launches": steps + 3}
 
 
+def cg_leg(plan, E, A, fx, dev, Bc, iters, peak):
+    """Secondary line: batched matrix-free Jacobi-CG (the linear solve of the Newton step on large meshes),
+    a fixed number of iterations.  Bytes per iteration and problem: the mat-vec (16*nelem + 32*nnode) plus
+    13 vector passes of the CG recurrences (16*nnode each)."""
+    import torch
+
+    from pinn_fem_b200 import ops
+
+    Ec, Ac = E[:, :Bc].contiguous(), A[:, :Bc].contiguous()
+    rhs = fx[:, None].expand(-1, Bc).contiguous()
+    ops.cg_solve(plan, Ec, Ac, rhs, rel_tol=0.0, max_iters=8)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, n_it, resid = ops.cg_solve(plan, Ec, Ac, rhs, rel_tol=0.0, max_iters=iters)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / n_it
+    ab = Bc * (16 * plan.nelem + 32 * plan.nnode + 13 * 16 * plan.nnode)
+    return {"problems": Bc, "iterations": n_it, "ms_per_iteration": ms,
+            "roofline": {"bound": "hbm", "achieved": ab / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": ab / (ms * 1e-3) / 1e9 / peak, "bytes_per_iteration": ab},
+            "gpu_launches": 7 * (n_it + 8) + 8}
+
+
 def cpu_reference_leg(steps, warmup, sample_problems=None):
     """Times the CPU restatement of the reference's element loop (oracle/pf_oracle.c, OpenMP over
     problems) on a bounded sample of the same workload: the full 999,941-element mesh, a slice of
@@ -344,6 +369,12 @@ def main():
             launches += extra["tangent_bsr"].pop("gpu_launches")
         except Exception as exc:
             extra["tangent_bsr"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if not args.no_tangent:
+        try:
+            extra["cg_solve"] = cg_leg(plan, E, A, fx, dev, min(B, 128), 40, peak)
+            launches += extra["cg_solve"].pop("gpu_launches")
+        except Exception as exc:
+            extra["cg_solve"] = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_gd:
         try:
             from pinn_fem_b200.bench_gd import gd_iterations_per_second

@@ -314,6 +314,23 @@ __global__ void column_sum_kernel(const double* __restrict__ part, int64_t rows,
     out[b] = scale * acc;
 }
 
+// Same sum for narrow batches: one CTA per column, 256 strided partial sums folded by a fixed tree
+// (a single thread walking ~10^3 rows serially costs more than the residual kernel itself at B = 1).
+__global__ void __launch_bounds__(256) column_sum_wide_kernel(const double* __restrict__ part, int64_t rows, int64_t ld,
+                                                              double scale, double* __restrict__ out) {
+    __shared__ double red[256];
+    const int64_t b = blockIdx.x;
+    double acc = 0.0;
+    for (int64_t r = threadIdx.x; r < rows; r += 256) acc += part[r * ld + b];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[b] = scale * red[0];
+}
+
 // ---------------------------------------------------------------------------
 // material VJP (element-centric, pure gather)
 // ---------------------------------------------------------------------------
@@ -623,8 +640,11 @@ static int launch_gather_generic(pf_plan* plan, int kind, int mode, int64_t ldb,
 #undef PF_GATHER_CALL2
     PF_CUDA_CHECK(cudaGetLastError());
     if (half_sq) {
-        column_sum_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(plan->d_work + b0, grid.x, ldb, nb, 0.5,
-                                                                        half_sq + b0);
+        if (nb <= 64)
+            column_sum_wide_kernel<<<(unsigned)nb, 256, 0, st>>>(plan->d_work + b0, grid.x, ldb, 0.5, half_sq + b0);
+        else
+            column_sum_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(plan->d_work + b0, grid.x, ldb, nb, 0.5,
+                                                                            half_sq + b0);
         PF_CUDA_CHECK(cudaGetLastError());
     }
     return PF_OK;

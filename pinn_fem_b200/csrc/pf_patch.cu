@@ -300,13 +300,22 @@ __global__ void __launch_bounds__(PatchCfg<CH>::kThreads, PatchCfg<CH>::kMinCtas
     }
 }
 
-__global__ void patch_column_sum_kernel(const double* __restrict__ part, int64_t rows, int64_t ld, int64_t ncol,
-                                        double scale, double* __restrict__ out) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= ncol) return;
+// out[b] = scale * sum over patches of part[patch][b]: a CTA per 32 columns, 32 strided partial sums per
+// column folded in a fixed order
+__global__ void __launch_bounds__(1024) patch_column_sum_kernel(const double* __restrict__ part, int64_t rows, int64_t ld,
+                                                                int64_t ncol, double scale, double* __restrict__ out) {
+    __shared__ double s[32][33];
+    const int64_t b = (int64_t)blockIdx.x * 32 + threadIdx.x;
     double acc = 0.0;
-    for (int64_t r = 0; r < rows; ++r) acc += part[r * ld + b];
-    out[b] = scale * acc;
+    if (b < ncol)
+        for (int64_t r = threadIdx.y; r < rows; r += 32) acc += part[r * ld + b];
+    s[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && b < ncol) {
+        double t = 0.0;
+        for (int y = 0; y < 32; ++y) t += s[y][threadIdx.x];
+        out[b] = scale * t;
+    }
 }
 
 template <int DIM, int MODE, bool MATB, bool STRAIN, bool BULK, int CH>
@@ -404,8 +413,8 @@ int pf_patch_gather(pf_plan* plan, const PfGatherCall& c, cudaStream_t st, int64
     if (rc) return rc;
     PF_CUDA_CHECK(cudaGetLastError());
     if (c.half_sq) {
-        patch_column_sum_kernel<<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(plan->d_work, npatch, c.ldb, ncol, 0.5,
-                                                                                c.half_sq);
+        patch_column_sum_kernel<<<(unsigned)((ncol + 31) / 32), dim3(32, 32), 0, st>>>(plan->d_work, npatch, c.ldb, ncol,
+                                                                                       0.5, c.half_sq);
         PF_CUDA_CHECK(cudaGetLastError());
     }
     *columns_done = ncol;

@@ -409,12 +409,23 @@ __global__ void cg_direction_kernel(CgVec v, const double* __restrict__ rz_new, 
     }
 }
 
-__global__ void cg_colsum_kernel(const double* __restrict__ part, int64_t rows, int64_t B, double* __restrict__ out) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+// out[b] = sum_rows part[row][b]: a CTA per 32 columns, 32 strided partial sums per column folded in a
+// fixed order (a single thread per column walking thousands of rows serially dominated the CG iteration)
+constexpr int CS_Y = 32;
+__global__ void __launch_bounds__(32 * CS_Y) cg_colsum_kernel(const double* __restrict__ part, int64_t rows, int64_t B,
+                                                              double* __restrict__ out) {
+    __shared__ double s[CS_Y][33];
+    const int64_t b = (int64_t)blockIdx.x * 32 + threadIdx.x;
     double acc = 0.0;
-    for (int64_t r = 0; r < rows; ++r) acc += part[r * B + b];
-    out[b] = acc;
+    if (b < B)
+        for (int64_t r = threadIdx.y; r < rows; r += CS_Y) acc += part[r * B + b];
+    s[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && b < B) {
+        double t = 0.0;
+        for (int y = 0; y < CS_Y; ++y) t += s[y][threadIdx.x];
+        out[b] = t;
+    }
 }
 
 }  // namespace
@@ -448,7 +459,8 @@ extern "C" int pf_cg_solve(pf_plan* plan, int kind, int64_t B, const double* u, 
     double* rr = bb + B;
     CgVec v{plan->d_dof_free, nd, B};
     dim3 blk(CG_BX, CG_BY), grd((unsigned)tiles, (unsigned)((B + CG_BX - 1) / CG_BX));
-    const unsigned cb = (unsigned)((B + 127) / 128);
+    const unsigned cb = (unsigned)((B + 31) / 32);
+    const dim3 cblk(32, CS_Y);
     {
         dim3 dblk(32, 8), dgrd((unsigned)((plan->nnode + 7) / 8), (unsigned)((B + 31) / 32));
         const int64_t ms = mat_batched ? B : 1, mb = mat_batched ? 1 : 0;
@@ -458,8 +470,8 @@ extern "C" int pf_cg_solve(pf_plan* plan, int kind, int64_t B, const double* u, 
             cg_diag_kernel<2><<<dgrd, dblk, 0, st>>>(plan->d_inc_ptr, plan->d_inc, plan->d_inc_geo, plan->d_dof_free, E, A, ms, mb, plan->nnode, B, dinv);
     }
     cg_init_kernel<<<grd, blk, 0, st>>>(v, rhs, dinv, x, r, p, part0, part1);
-    cg_colsum_kernel<<<cb, 128, 0, st>>>(part0, tiles, B, rz);
-    cg_colsum_kernel<<<cb, 128, 0, st>>>(part1, tiles, B, bb);
+    cg_colsum_kernel<<<cb, cblk, 0, st>>>(part0, tiles, B, rz);
+    cg_colsum_kernel<<<cb, cblk, 0, st>>>(part1, tiles, B, bb);
     PF_CUDA_CHECK(cudaGetLastError());
     std::vector<double> h_rr(B), h_bb(B);
     PF_CUDA_CHECK(cudaMemcpyAsync(h_bb.data(), bb, B * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -472,10 +484,10 @@ extern "C" int pf_cg_solve(pf_plan* plan, int kind, int64_t B, const double* u, 
         rc = pf_tangent_matvec(plan, kind, B, u, E, A, mat_batched, p, Ap, stream);
         if (rc) return rc;
         cg_dot_kernel<<<grd, blk, 0, st>>>(v, p, Ap, part0);
-        cg_colsum_kernel<<<cb, 128, 0, st>>>(part0, tiles, B, pAp);
+        cg_colsum_kernel<<<cb, cblk, 0, st>>>(part0, tiles, B, pAp);
         cg_update_kernel<<<grd, blk, 0, st>>>(v, rz, pAp, p, Ap, dinv, x, r, part0, part1);
-        cg_colsum_kernel<<<cb, 128, 0, st>>>(part0, tiles, B, rz_new);
-        cg_colsum_kernel<<<cb, 128, 0, st>>>(part1, tiles, B, rr);
+        cg_colsum_kernel<<<cb, cblk, 0, st>>>(part0, tiles, B, rz_new);
+        cg_colsum_kernel<<<cb, cblk, 0, st>>>(part1, tiles, B, rr);
         cg_direction_kernel<<<grd, blk, 0, st>>>(v, rz_new, rz, r, dinv, p);
         std::swap(rz, rz_new);
         ++it;
