@@ -8,7 +8,7 @@
 //   forward   z_l[t][o]   = sum_i a_l[i][t]  Wt_l[i][o]     M = points, N = out, K = in
 //   backprop  e_l[t][i]   = sum_o D_l[o][t]  W_l[o][i]      M = points, N = in,  K = out
 //   gradient  dW_l[o][i]  = sum_t D_l[o][t]  a_l[i][t]      M = out,    N = in + 1 (ones row -> bias), K = points
-// A CTA (4 warps) is persistent over tiles of 128 points.  Each warp owns 32 points through the
+// A CTA (8 warps) is persistent over tiles of 128 points.  Each warp owns 16 points through the
 // forward and backprop GEMMs (no block barrier); the gradient GEMMs span all 128 points, their output
 // tiles are dealt to the warps and added into a per-CTA accumulator in shared memory, so the
 // reduction order is fixed: tile order inside a CTA, CTA order across the grid (reduce_rows).
@@ -21,8 +21,10 @@ namespace {
 
 constexpr int PTS = 128;      // points per tile
 constexpr int PS = PTS + 4;   // activation row stride (doubles): 264 words = 8 (mod 32)
-constexpr int kThreads = 128;
-constexpr int kWarps = kThreads / 32;
+constexpr int kWarps = 8;              // warps per CTA: each owns PTS / kWarps points of a tile
+constexpr int kThreads = kWarps * 32;
+constexpr int WPTS = PTS / kWarps;     // points per warp (16)
+constexpr int MTW = WPTS / 8;          // m8 tiles per warp (2)
 
 __host__ __device__ inline int ceil4(int x) { return (x + 3) & ~3; }
 __host__ __device__ inline int ceil8(int x) { return (x + 7) & ~7; }
@@ -94,15 +96,15 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// C[t][n] (+)= sum_k A[k][t] B[k][n] for the calling warp's 32 points (4 m-tiles) and one n-tile.
+// C[t][n] (+)= sum_k A[k][t] B[k][n] for the calling warp's points (MTW m-tiles) and one n-tile.
 // A is [k][point] with stride PS, B is [k][n] with stride ldb.
 __device__ __forceinline__ void warp_gemm_tile(const double* __restrict__ A, const double* __restrict__ Bm, int ldb,
-                                               int K, int tw0, int n0, int g, int t4, double (&c)[4][2]) {
+                                               int K, int tw0, int n0, int g, int t4, double (&c)[MTW][2]) {
     for (int k0 = 0; k0 < K; k0 += 4) {
         const double b = Bm[(k0 + t4) * ldb + n0 + g];
         const double* ap = A + (k0 + t4) * PS + tw0 + g;
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) dmma(c[mt][0], c[mt][1], ap[mt * 8], b);
+        for (int mt = 0; mt < MTW; ++mt) dmma(c[mt][0], c[mt][1], ap[mt * 8], b);
     }
 }
 
@@ -156,16 +158,19 @@ __global__ void __launch_bounds__(kThreads) mlp_tc_kernel(PfMlpDesc d, const dou
     if (tid == 0) sm[s.bo_off] = theta[d.b_off[L]];
     // ones row of every hidden block (bias gradients); when w is a multiple of 8 the forward epilogue
     // never touches it, otherwise it rewrites it every tile
-    for (int l = 1; l <= L; ++l) sm[s.act_off[l] + w * PS + tid] = 1.0;
+    for (int l = 1; l <= L; ++l)
+        for (int t = tid; t < PTS; t += kThreads) sm[s.act_off[l] + w * PS + t] = 1.0;
     __syncthreads();
 
     const int64_t ntiles = (n + PTS - 1) / PTS;
-    const int tw0 = warp * 32;  // first point of the warp inside the tile
+    const int tw0 = warp * WPTS;        // first point of the warp inside the tile
+    const bool ptlane = lane < WPTS;     // per-point phases: lane i of a warp handles the warp's point i
+    const int pt = tw0 + (ptlane ? lane : 0);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t p = tile * PTS + tid;
+        const int64_t p = tile * PTS + pt;
         // ---- inputs: [load_factor, x_c(, y_c)] (sorted dict keys of fem/properties.py:116-125), ones row ----
-        {
-            double* a0 = sm + s.act_off[0] + tid;
+        if (ptlane) {
+            double* a0 = sm + s.act_off[0] + pt;
             if (X) {
                 for (int i = 0; i < d.in_dim; ++i) a0[i * PS] = p < n ? X[p * d.in_dim + i] : 0.0;
             } else {
@@ -181,16 +186,16 @@ __global__ void __launch_bounds__(kThreads) mlp_tc_kernel(PfMlpDesc d, const dou
             const double* A = sm + s.act_off[l];
             double* An = sm + s.act_off[l + 1];
             for (int n0 = 0; n0 < w8; n0 += 8) {
-                double c[4][2];
+                double c[MTW][2];
                 const double b0 = sm[s.b_off[l] + n0 + 2 * t4], b1 = sm[s.b_off[l] + n0 + 2 * t4 + 1];
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
+                for (int mt = 0; mt < MTW; ++mt) {
                     c[mt][0] = b0;
                     c[mt][1] = b1;
                 }
                 warp_gemm_tile(A, sm + s.wt_off[l], s.WS, K, tw0, n0, g, t4, c);
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
+                for (int mt = 0; mt < MTW; ++mt)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int o = n0 + 2 * t4 + h;
@@ -201,20 +206,20 @@ __global__ void __launch_bounds__(kThreads) mlp_tc_kernel(PfMlpDesc d, const dou
             __syncwarp();
         }
         // ---- output layer, softplus, dL/dz ----
-        const double* aL = sm + s.act_off[L] + tid;
+        const double* aL = sm + s.act_off[L] + pt;
         double z = sm[s.bo_off];
         for (int i = 0; i < w; ++i) z = fma(sm[s.wo_off + i], aL[i * PS], z);
         if (!BWD) {
-            if (p < n) out[p] = pf_mlp_output(z, scale, positive);
+            if (ptlane && p < n) out[p] = pf_mlp_output(z, scale, positive);
             __syncwarp();
             continue;
         }
-        const double dz = p < n ? g_out[p] * pf_mlp_output_grad(z, scale, positive) : 0.0;
-        sm[s.dz_off + tid] = dz;
+        const double dz = (ptlane && p < n) ? g_out[p] * pf_mlp_output_grad(z, scale, positive) : 0.0;
+        if (ptlane) sm[s.dz_off + pt] = dz;
         // delta of the last hidden layer; D_l lives in the delta buffer (l = L-1) or in the dead block l+2
         auto dptr = [&](int l) { return sm + (l == L - 1 ? s.d_off : s.act_off[l + 2]); };
-        {
-            double* D = dptr(L - 1) + tid;
+        if (ptlane) {
+            double* D = dptr(L - 1) + pt;
             for (int o = 0; o < w8; ++o) {
                 const double a = aL[o * PS];
                 D[o * PS] = sm[s.wo_off + o] * dz * (1.0 - a * a);  // rows >= w: zero weight
@@ -267,10 +272,12 @@ __global__ void __launch_bounds__(kThreads) mlp_tc_kernel(PfMlpDesc d, const dou
                 // the ones row (i = w) gives 1 - 1 = 0, padded columns have zero weights.
                 double* Dn = dptr(l - 1);
                 for (int n0 = 0; n0 < w8; n0 += 8) {
-                    double c[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+                    double c[MTW][2];
+#pragma unroll
+                    for (int mt = 0; mt < MTW; ++mt) c[mt][0] = c[mt][1] = 0.0;
                     warp_gemm_tile(D, sm + s.wn_off[l], s.WSI, ceil4(w), tw0, n0, g, t4, c);
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
+                    for (int mt = 0; mt < MTW; ++mt)
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int i = n0 + 2 * t4 + h;
