@@ -150,6 +150,42 @@ def tangent_leg(plan, E, A, dev, Bt, steps, peak):
                          "algorithmic_bytes_per_launch": ab}, "gpu_launches": steps + 3}
 
 
+def jtj_leg(dev, n, m, peak_note="fp64 tensor (DMMA); B200 datasheet 40 TFLOP/s, not in MEASURED_PEAKS.json"):
+    """Secondary line: Gauss-Newton normal equations J^T J + damping (fem/nn_solver.py:268-274) on a random
+    full-rank J ~ N(0,1) (SURVEY 8d, C4 scaled variant) and the LU solve of the damped system."""
+    import torch
+
+    from pinn_fem_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(0)
+    J = torch.randn((m, n), generator=g, device=dev, dtype=torch.float64)
+    R = torch.randn(m, generator=g, device=dev, dtype=torch.float64)
+    out = {"m": m, "n": n}
+    for name, fn in (("jtj", lambda: ops.gn_normal_equations(J, R)),):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            jtj, jtr, _ = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 3
+        out["jtj_ms"] = ms
+        out["jtj_tflops_full_2mn2"] = 2.0 * m * n * n / (ms * 1e-3) / 1e12
+        out["jtj_tflops_executed"] = out["jtj_tflops_full_2mn2"] * (n / 64 + 1) / (2 * (n / 64))  # upper tiles only
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    dx = ops.solve_dense(jtj, -jtr)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    out["lu_solve_ms"] = e0.elapsed_time(e1)
+    out["lu_tflops"] = (2.0 / 3.0) * n ** 3 / (out["lu_solve_ms"] * 1e-3) / 1e12
+    out["peak_note"] = peak_note
+    out["gpu_launches"] = 4 * 3 + 4 * (n // 32 + 1)
+    return out
+
+
 def cg_leg(plan, E, A, fx, dev, Bc, iters, peak):
     """Secondary line: batched matrix-free Jacobi-CG (the linear solve of the Newton step on large meshes),
     a fixed number of iterations.  Bytes per iteration and problem: the mat-vec (16*nelem + 32*nnode) plus
@@ -375,6 +411,12 @@ def main():
             launches += extra["cg_solve"].pop("gpu_launches")
         except Exception as exc:
             extra["cg_solve"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if not args.no_tangent:
+        try:
+            extra["gauss_newton"] = jtj_leg(dev, 4096, 4096)
+            launches += extra["gauss_newton"].pop("gpu_launches")
+        except Exception as exc:
+            extra["gauss_newton"] = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_gd:
         try:
             from pinn_fem_b200.bench_gd import gd_iterations_per_second

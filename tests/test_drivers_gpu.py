@@ -117,6 +117,22 @@ def test_fem2d_like_incremental_newton(golden_dir):
     assert abs(np.max(np.linalg.norm(res.displacements, axis=1)) - 6.344508621253013e-4) < 1e-11
 
 
+def test_incremental_newton_through_matrix_free_cg(golden_dir, monkeypatch):
+    """Large meshes solve the Newton step with the matrix-free batched CG instead of dense LU; forcing that
+    path on fem2d_like must reproduce the reference's displacements to the same 1e-8."""
+    from pinn_fem_b200.fem import FEMModel, Material, SolverConfig, core, solve_incremental_newton
+
+    monkeypatch.setattr(core, "DENSE_LIMIT", 0)
+    g = np.load(golden_dir / "fem2d_like_nr.npz")
+    model = FEMModel(nodes=g["nodes"], elements=g["elements"], material=Material(young=float(g["young"]), area=float(g["area"]), density=7800.0),
+                     loads=g["loads"], fixed_dofs=g["fixed"])
+    res = solve_incremental_newton(model, SolverConfig(n_increments=10, max_iterations=120, tolerance=1e-5))
+    assert res.converged == bool(g["converged"])
+    assert rel(res.displacements.reshape(-1), g["u"]) < 1e-8
+    assert rel(res.reactions.reshape(-1), g["reactions"]) < 1e-8
+    assert [h["iterations"] for h in res.history] == g["iterations"].tolist()
+
+
 def test_assemble_system_numpy_api(assembly_golden):
     from pinn_fem_b200.fem import FEMModel, Material
     from pinn_fem_b200.fem.assembly import assemble_system
