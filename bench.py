@@ -442,7 +442,8 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (torch.Generator seed 1234+rank: u~U(-1e-3,1e-3), E,A~U(0.5,1.5), lambda=1)",
                 "config": config, "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e,
-                "gpu_launches": launches, "clocks": clocks}
+                "gpu_launches": args.steps,  # timed region: exactly one patch_gather_kernel launch per step
+                "gpu_launches_all_legs": launches, "clocks": clocks}
         line.update(extra)
         print(json.dumps(line))
     if world > 1:
