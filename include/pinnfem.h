@@ -220,6 +220,54 @@ int pf_gd_solve(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, double* t
                 int32_t* n_iters, int32_t* converged, double* reactions, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Element-sharded meshes over the GPUs of one box (one process per GPU).
+ * A rank's local mesh lists its owned nodes first, then its halo nodes, and
+ * holds every element incident to an owned node in ascending global element
+ * id, so the owned rows of f_int carry the same bits as on a single GPU.
+ * NCCL (resolved with dlopen at first use) moves the halo rows between
+ * neighbours and all-reduces dL/dtheta and the loss scalars.  The reference
+ * has no counterpart: its dense K cannot hold such meshes (fem/assembly.py:19).
+ *
+ *   pf_comm_unique_id   rank 0 creates the 128-byte NCCL id, the host
+ *                       broadcasts it (torch.distributed), every rank calls
+ *                       pf_comm_create(world, rank, id, device)
+ *   pf_halo_create      peers[n_peers]; send_ptr/recv_ptr [n_peers+1] offsets
+ *                       into send_nodes / recv_nodes (host int32, LOCAL node ids)
+ *   pf_halo_exchange    x dev [ndof_local][B]: owned rows on the send lists go
+ *                       out, halo rows are overwritten with the owners' values
+ * ------------------------------------------------------------------------ */
+typedef struct pf_comm pf_comm;
+typedef struct pf_halo pf_halo;
+int pf_comm_available(void);
+int pf_comm_unique_id(unsigned char* id128);
+int pf_comm_create(int world, int rank, const unsigned char* id128, int device, pf_comm** out);
+void pf_comm_destroy(pf_comm* comm);
+int pf_comm_allreduce_sum(pf_comm* comm, double* buf, int64_t n, void* stream);
+int pf_halo_create(pf_comm* comm, int dim, int n_peers, const int32_t* peers, const int64_t* send_ptr,
+                   const int32_t* send_nodes, const int64_t* recv_ptr, const int32_t* recv_nodes, pf_halo** out);
+void pf_halo_destroy(pf_halo* halo);
+int pf_halo_exchange(pf_halo* halo, double* x, int64_t B, void* stream);
+
+typedef struct pf_gd_shard {
+    pf_halo* halo;              /* exchange lists of this rank */
+    int64_t n_owned_nodes;      /* owned nodes come first in the local numbering */
+    const uint8_t* elem_owned;  /* dev [nelem_local]: 1 where this rank owns the element (owner of its first node) */
+    int64_t nfree_global;       /* free DOFs of the whole mesh (divisor of the legacy mean loss) */
+    int32_t n_measured_global;  /* measurements of the whole mesh; cfg->n_measured counts this rank's */
+    int32_t reserved;
+} pf_gd_shard;
+
+/* pf_gd_solve's large-mesh loop on this rank's local mesh (plan built from it): theta dev [n_theta]
+ * (replicated, identical on every rank on return), u_local dev [ndof_local], f_ext_local dev [ndof_local],
+ * meas_dofs_local / meas_vals_local: the measurements on this rank's owned DOFs (local DOF ids),
+ * history dev [max_iterations][PF_GD_HISTORY_COLS] (identical on every rank), reactions_local dev
+ * [ndof_local] (owned rows).  Every rank must call it. */
+int pf_gd_solve_sharded(pf_plan* plan, const pf_gd_config* cfg, const pf_gd_shard* shard, double* theta,
+                        double* u_local, const double* f_ext_local, const int32_t* meas_dofs_local,
+                        const double* meas_vals_local, double* history, int32_t* n_iters, int32_t* converged,
+                        double* reactions_local, void* stream);
+
+/* ------------------------------------------------------------------------
  * Linear solves.
  * pf_solve_dense: batched dense solve A x = b by LU with partial pivoting
  *   (np.linalg.solve in fem/core.py:35, fem/solver.py:464; torch.linalg.solve

@@ -51,6 +51,19 @@ class GDConfig(C.Structure):
     ]
 
 
+class GDShard(C.Structure):
+    """Mirror of ``pf_gd_shard`` (include/pinnfem.h)."""
+
+    _fields_ = [
+        ("halo", C.c_void_p),
+        ("n_owned_nodes", C.c_int64),
+        ("elem_owned", C.c_void_p),
+        ("nfree_global", C.c_int64),
+        ("n_measured_global", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 _vp, _i64, _i32, _dbl, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int
 
 # name -> (restype, argtypes); must list every symbol of include/pinnfem.h
@@ -83,6 +96,16 @@ SIGNATURES = {
     "pf_gn_normal_equations": (_int, [_i64, _i64, _vp, _vp, _dbl, _vp, _vp, _vp, _vp]),
     "pf_gn_jacobian": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _dbl, _dbl, _vp, _i64, _vp, _vp]),
     "pf_residual_host": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _vp, _dbl, _vp, _i64]),
+    "pf_comm_available": (_int, []),
+    "pf_comm_unique_id": (_int, [_vp]),
+    "pf_comm_create": (_int, [_int, _int, _vp, _int, C.POINTER(_vp)]),
+    "pf_comm_destroy": (None, [_vp]),
+    "pf_comm_allreduce_sum": (_int, [_vp, _vp, _i64, _vp]),
+    "pf_halo_create": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "pf_halo_destroy": (None, [_vp]),
+    "pf_halo_exchange": (_int, [_vp, _vp, _i64, _vp]),
+    "pf_gd_solve_sharded": (_int, [_vp, C.POINTER(GDConfig), C.POINTER(GDShard), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _vp]),
 }
 
 _lib = None

@@ -607,7 +607,7 @@ extern "C" int pf_gd_solve(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob
     const size_t smem = (size_t)off * sizeof(double);
     if (smem > 200 * 1024)  // does not fit one CTA: the multi-kernel device-resident loop (pf_gd_large.cu)
         return pf_gd_solve_large(plan, cfg, nprob, theta, u, f_ext, meas_dofs, meas_vals, history, n_iters, converged,
-                                 reactions, pf_stream_of(stream));
+                                 reactions, pf_stream_of(stream), nullptr);
     if (smem > 48 * 1024)
         PF_CUDA_CHECK(cudaFuncSetAttribute(gd_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int work = std::max({a.nelem * max_w, a.ndof, max_w * max_w + max_w, 32});

@@ -8,6 +8,12 @@
 // (losses, norms, the converged flag, beta^t) living in device memory.  The host only enqueues; it
 // looks at the converged flag every kPoll iterations.  After convergence the remaining enqueued
 // iterations are no-ops for the state (the update kernels test the flag).
+//
+// Element-sharded meshes (pf_gd_solve_sharded): every rank runs the same sequence on its local mesh
+// (owned nodes first, then halo nodes; all elements incident to an owned node).  Per iteration the
+// ranks swap the halo rows of u and of r (pf_halo_exchange) and all-reduce ONE buffer
+// [dL/dtheta | 0.5 sum r^2 | sum data^2 | sum u_free^2]; theta, the losses, the history and the
+// convergence flag are then identical on every rank.
 #include <algorithm>
 #include <vector>
 
@@ -20,17 +26,20 @@ constexpr int kPoll = 8;
 constexpr int kRedThreads = 256;
 
 // device scalars
-enum { S_HALF_SQ = 0, S_DATA_SQ, S_UNORM_SQ, S_POW_B1, S_POW_B2, S_DONE, S_ITERS, S_CONV, S_TN, S_COUNT };
+enum { S_POW_B1 = 0, S_POW_B2, S_DONE, S_ITERS, S_CONV, S_COUNT };
+// reduction buffer: [n_theta gradient entries | L_HALF_SQ | L_DATA_SQ | L_UNORM_SQ]
+enum { L_HALF_SQ = 0, L_DATA_SQ, L_UNORM_SQ, L_COUNT };
 
 struct LargeCfg {
     double tolerance, lr_u, lr_t, alpha_p, alpha_d, load_factor, gscale, cdata;
-    int legacy, has_meas, n_meas, nfree, max_iterations;
+    int legacy, has_meas, n_meas, max_iterations;  // n_meas, nfree: of the whole mesh
+    int64_t nfree;
 };
 
 // sum_j (m_j - u[dof_j])^2 in a fixed order (one block)
 __global__ void __launch_bounds__(kRedThreads) data_loss_kernel(const int32_t* __restrict__ md,
                                                                 const double* __restrict__ mv, int n_meas,
-                                                                const double* __restrict__ u, double* __restrict__ sc) {
+                                                                const double* __restrict__ u, double* __restrict__ losses) {
     __shared__ double red[kRedThreads];
     double s = 0.0;
     for (int j = threadIdx.x; j < n_meas; j += kRedThreads) {
@@ -43,7 +52,7 @@ __global__ void __launch_bounds__(kRedThreads) data_loss_kernel(const int32_t* _
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) sc[S_DATA_SQ] = red[0];
+    if (threadIdx.x == 0) losses[L_DATA_SQ] = red[0];
 }
 
 // Adam on u (torch defaults), data-loss gradient, BC zeroing (solver.py:292-298), partial ||u_free||^2
@@ -95,6 +104,7 @@ struct TensorList {
 __global__ void __launch_bounds__(1024) adam_theta_finish_kernel(LargeCfg c, int n_active, int n_theta, TensorList tl,
                                                                  const double* __restrict__ g, double* __restrict__ theta,
                                                                  double* __restrict__ m, double* __restrict__ v,
+                                                                 const double* __restrict__ losses,
                                                                  const double* __restrict__ upart, int n_upart,
                                                                  double* __restrict__ sc, double* __restrict__ history) {
     __shared__ double tn[3 * 2 * (PF_MLP_MAX_LAYERS + 1)];
@@ -125,12 +135,12 @@ __global__ void __launch_bounds__(1024) adam_theta_finish_kernel(LargeCfg c, int
     if (threadIdx.x == 0 && !done) {
         double tsum = 0.0;
         for (int t = 0; t < tl.n; ++t) tsum += tn[t];
-        double un = 0.0;
+        double un = n_upart ? 0.0 : losses[L_UNORM_SQ];  // sharded runs pre-reduce ||u_free||^2 into the buffer
         for (int b = 0; b < n_upart; ++b) un += upart[b];
         const int it = (int)sc[S_ITERS];  // 0-based index of this iteration
-        const double s2 = 2.0 * sc[S_HALF_SQ];
+        const double s2 = 2.0 * losses[L_HALF_SQ];
         const double loss_p = c.legacy ? s2 / (double)c.nfree : 0.5 * s2;
-        const double loss_d = c.has_meas ? sc[S_DATA_SQ] / c.n_meas : 0.0;
+        const double loss_d = c.has_meas ? losses[L_DATA_SQ] / c.n_meas : 0.0;
         const double loss = c.alpha_p * loss_p + (c.has_meas ? c.alpha_d * loss_d : 0.0);
         const double rn = sqrt(s2);
         if (history) {
@@ -157,6 +167,41 @@ __global__ void __launch_bounds__(1024) adam_theta_finish_kernel(LargeCfg c, int
         } else if (it + 1 >= c.max_iterations) {
             sc[S_DONE] = 1.0;
         }
+    }
+}
+
+// part[block] = sum of x^2 over the block's grid-stride slice (fixed order)
+__global__ void __launch_bounds__(kRedThreads) sq_partial_kernel(const double* __restrict__ x, int64_t n,
+                                                                 double* __restrict__ part) {
+    __shared__ double red[kRedThreads];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kRedThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kRedThreads)
+        s += x[i] * x[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+// out = scale * sum(part[0..n)) in ascending order
+__global__ void sum_partials_kernel(const double* __restrict__ part, int n, double scale, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += part[i];
+        *out = scale * s;
+    }
+}
+
+// elements on a partition interface are local to both ranks: only the owner contributes to dL/dtheta
+__global__ void mask_elements_kernel(const uint8_t* __restrict__ owned, int64_t n, double* __restrict__ gE,
+                                     double* __restrict__ gA) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !owned[i]) {
+        gE[i] = 0.0;
+        gA[i] = 0.0;
     }
 }
 
@@ -189,11 +234,17 @@ struct DevBuf {
 
 }  // namespace
 
-// One problem at a time; called by pf_gd_solve when the single-CTA kernel does not fit.
+// One problem at a time; called by pf_gd_solve when the single-CTA kernel does not fit (sh == NULL)
+// and by pf_gd_solve_sharded with this rank's local mesh.
 int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, double* theta_all, double* u_all,
                       const double* f_ext, const int32_t* meas_dofs, const double* meas_vals_all, double* history_all,
-                      int32_t* n_iters, int32_t* converged, double* reactions_all, cudaStream_t st) {
+                      int32_t* n_iters, int32_t* converged, double* reactions_all, cudaStream_t st,
+                      const pf_gd_shard* sh) {
     const int64_t ndof = plan->ndof, nelem = plan->nelem;
+    const int64_t nd_own = sh ? sh->n_owned_nodes * plan->dim : ndof;  // rows this rank updates
+    pf_comm* comm = sh ? pf_halo_comm(sh->halo) : nullptr;
+    PF_REQUIRE(!sh || (sh->halo && nprob == 1 && sh->n_owned_nodes >= 0 && sh->n_owned_nodes <= plan->nnode),
+               "pf_gd_solve_sharded: bad shard description");
     PfMlpDesc desc[3];
     int theta_off[3] = {0, 0, 0}, ntheta = 0;
     TensorList tl{};
@@ -216,8 +267,11 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
     }
     // density never enters the physics: its gradient is None in the reference and Adam skips it
     const int n_active = cfg->net_enabled[2] ? theta_off[2] : ntheta;
-    const int n_meas = cfg->n_measured;
-    const bool has_meas = n_meas > 0 && meas_dofs && meas_vals_all && cfg->alpha_data > 0.0;
+    const int n_meas = cfg->n_measured;                                   // measurements this rank holds
+    const int n_meas_all = sh ? sh->n_measured_global : n_meas;           // of the whole mesh (the mean's divisor)
+    const bool has_meas = n_meas_all > 0 && cfg->alpha_data > 0.0 && (sh || (meas_dofs && meas_vals_all));
+    const bool local_meas = has_meas && n_meas > 0 && meas_dofs && meas_vals_all;
+    const int64_t nfree_all = sh ? sh->nfree_global : plan->nfree;
 
     LargeCfg c{};
     c.tolerance = cfg->tolerance;
@@ -227,11 +281,11 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
     c.alpha_d = cfg->alpha_data;
     c.load_factor = cfg->load_factor;
     c.legacy = cfg->loss_mode == 1;
-    c.gscale = c.legacy ? 2.0 * cfg->alpha_physics / (double)plan->nfree : cfg->alpha_physics;
+    c.gscale = c.legacy ? 2.0 * cfg->alpha_physics / (double)nfree_all : cfg->alpha_physics;
     c.has_meas = has_meas ? 1 : 0;
-    c.n_meas = n_meas;
-    c.cdata = has_meas ? -2.0 * cfg->alpha_data / n_meas : 0.0;
-    c.nfree = (int)plan->nfree;
+    c.n_meas = n_meas_all;
+    c.cdata = has_meas ? -2.0 * cfg->alpha_data / n_meas_all : 0.0;
+    c.nfree = nfree_all;
     c.max_iterations = cfg->max_iterations;
 
     DevBuf buf;
@@ -240,7 +294,7 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
     if ((rc = buf.alloc(&E, nelem)) || (rc = buf.alloc(&A, nelem)) || (rc = buf.alloc(&r, ndof)) ||
         (rc = buf.alloc(&gu, ndof)) || (rc = buf.alloc(&gE, nelem)) || (rc = buf.alloc(&gA, nelem)) ||
         (rc = buf.alloc(&mu, ndof)) || (rc = buf.alloc(&vu, ndof)) || (rc = buf.alloc(&mt, ntheta)) ||
-        (rc = buf.alloc(&vt, ntheta)) || (rc = buf.alloc(&gt, ntheta)) || (rc = buf.alloc(&sc, S_COUNT)) ||
+        (rc = buf.alloc(&vt, ntheta)) || (rc = buf.alloc(&gt, ntheta + L_COUNT)) || (rc = buf.alloc(&sc, S_COUNT)) ||
         (rc = buf.alloc(&fint, ndof)))
         return rc;
     const int ublocks = (int)std::min<int64_t>((ndof + kRedThreads - 1) / kRedThreads, 1024);
@@ -260,7 +314,8 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
 
     std::vector<int32_t> h_md;
     std::vector<double> h_mv, h_sum, h_cnt;
-    if (has_meas) {
+    double* losses = gt + ntheta;  // tail of the reduction buffer
+    if (local_meas) {
         h_md.resize(n_meas);
         PF_CUDA_CHECK(cudaMemcpyAsync(h_md.data(), meas_dofs, n_meas * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         PF_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -273,16 +328,18 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
     for (int64_t p = 0; p < nprob; ++p) {
         double* theta = theta_all ? theta_all + p * ntheta : nullptr;
         double* u = u_all + p * ndof;
-        const double* mv = has_meas ? meas_vals_all + p * n_meas : nullptr;
+        const double* mv = local_meas ? meas_vals_all + p * n_meas : nullptr;
         double* history = history_all ? history_all + p * (int64_t)std::max(cfg->max_iterations, 1) * PF_GD_HISTORY_COLS
                                       : nullptr;
         if (has_meas) {  // per-DOF sums of the targets: d/du of mean((m - u)^2) in closed form
             h_mv.resize(n_meas);
-            PF_CUDA_CHECK(cudaMemcpyAsync(h_mv.data(), mv, n_meas * sizeof(double), cudaMemcpyDeviceToHost, st));
-            PF_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (local_meas) {
+                PF_CUDA_CHECK(cudaMemcpyAsync(h_mv.data(), mv, n_meas * sizeof(double), cudaMemcpyDeviceToHost, st));
+                PF_CUDA_CHECK(cudaStreamSynchronize(st));
+            }
             h_sum.assign(ndof, 0.0);
             h_cnt.assign(ndof, 0.0);
-            for (int j = 0; j < n_meas; ++j) {
+            for (int j = 0; j < (local_meas ? n_meas : 0); ++j) {
                 h_sum[h_md[j]] += h_mv[j];
                 h_cnt[h_md[j]] += 1.0;
             }
@@ -294,8 +351,8 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
         if (ntheta) {
             PF_CUDA_CHECK(cudaMemsetAsync(mt, 0, ntheta * sizeof(double), st));
             PF_CUDA_CHECK(cudaMemsetAsync(vt, 0, ntheta * sizeof(double), st));
-            PF_CUDA_CHECK(cudaMemsetAsync(gt, 0, ntheta * sizeof(double), st));
         }
+        PF_CUDA_CHECK(cudaMemsetAsync(gt, 0, (ntheta + L_COUNT) * sizeof(double), st));
         for (int i = 0; i < S_COUNT; ++i) h_sc[i] = 0.0;
         h_sc[S_POW_B1] = h_sc[S_POW_B2] = 1.0;
         if (cfg->max_iterations == 0) h_sc[S_DONE] = 1.0;
@@ -320,13 +377,26 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
         for (int it = 0; it < cfg->max_iterations && !finished; ++it) {
             if ((rc = materials())) return rc;
             // r = f_int - lambda f_ext on free DOFs, 0.5 sum r^2 (solver.py:262-270)
-            if ((rc = pf_residual(plan, PF_ELEM_LINEAR, 1, u, E, A, 0, nullptr, f_ext, 0, cfg->load_factor, r,
-                                  sc + S_HALF_SQ, nullptr, st)))
-                return rc;
+            if (!sh) {
+                if ((rc = pf_residual(plan, PF_ELEM_LINEAR, 1, u, E, A, 0, nullptr, f_ext, 0, cfg->load_factor, r,
+                                      losses + L_HALF_SQ, nullptr, st)))
+                    return rc;
+            } else {
+                if ((rc = pf_halo_exchange(sh->halo, u, 1, st))) return rc;  // neighbours' latest u on the halo rows
+                if ((rc = pf_residual(plan, PF_ELEM_LINEAR, 1, u, E, A, 0, nullptr, f_ext, 0, cfg->load_factor, r, nullptr,
+                                      nullptr, st)))
+                    return rc;
+                // halo rows of the local residual are incomplete sums: drop them, then fetch the owners' values
+                if (ndof > nd_own) PF_CUDA_CHECK(cudaMemsetAsync(r + nd_own, 0, (ndof - nd_own) * sizeof(double), st));
+                sq_partial_kernel<<<ublocks, kRedThreads, 0, st>>>(r, nd_own, upart);
+                sum_partials_kernel<<<1, 32, 0, st>>>(upart, ublocks, 0.5, losses + L_HALF_SQ);
+                if ((rc = pf_halo_exchange(sh->halo, r, 1, st))) return rc;
+            }
             // reverse pass: dL/du = gscale K r, dL/dE, dL/dA, dL/dtheta (closed form of the autograd graph)
             if ((rc = pf_tangent_matvec(plan, PF_ELEM_LINEAR, 1, nullptr, E, A, 0, r, gu, st))) return rc;
             if (n_active) {
                 if ((rc = pf_material_vjp(plan, PF_ELEM_LINEAR, 1, u, E, A, 0, r, gE, gA, st))) return rc;
+                if (sh && sh->elem_owned) mask_elements_kernel<<<eb, 256, 0, st>>>(sh->elem_owned, nelem, gE, gA);
                 for (int k = 0; k < 2; ++k)
                     if (cfg->net_enabled[k] &&
                         (rc = pf_mlp_backward(plan, desc[k].in_dim, desc[k].L, desc[k].w, theta + theta_off[k], nelem,
@@ -334,10 +404,14 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
                                               gt + theta_off[k], st)))
                         return rc;
             }
-            if (has_meas) data_loss_kernel<<<1, kRedThreads, 0, st>>>(meas_dofs, mv, n_meas, u, sc);
-            adam_u_kernel<<<ublocks, kRedThreads, 0, st>>>(c, ndof, gu, msum, mcnt, plan->d_dof_free, u, mu, vu, sc, upart);
-            adam_theta_finish_kernel<<<1, 1024, 0, st>>>(c, n_active, ntheta, tl, gt, theta, mt, vt, upart, ublocks, sc,
-                                                        history);
+            if (local_meas) data_loss_kernel<<<1, kRedThreads, 0, st>>>(meas_dofs, mv, n_meas, u, losses);
+            adam_u_kernel<<<ublocks, kRedThreads, 0, st>>>(c, nd_own, gu, msum, mcnt, plan->d_dof_free, u, mu, vu, sc, upart);
+            if (sh) {  // one all-reduce per iteration: [dL/dtheta | 0.5 sum r^2 | sum data^2 | sum u_free^2]
+                sum_partials_kernel<<<1, 32, 0, st>>>(upart, ublocks, 1.0, losses + L_UNORM_SQ);
+                if ((rc = pf_comm_allreduce_sum(comm, gt, ntheta + L_COUNT, st))) return rc;
+            }
+            adam_theta_finish_kernel<<<1, 1024, 0, st>>>(c, n_active, ntheta, tl, gt, theta, mt, vt, losses, upart,
+                                                        sh ? 0 : ublocks, sc, history);
             PF_CUDA_CHECK(cudaGetLastError());
             if ((it + 1) % kPoll == 0 || it + 1 == cfg->max_iterations) {
                 PF_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
@@ -352,15 +426,31 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
         const int32_t iters = (int32_t)h_sc[S_ITERS], conv = (int32_t)h_sc[S_CONV];
         PF_CUDA_CHECK(cudaMemcpyAsync(n_iters + p, &iters, sizeof(int32_t), cudaMemcpyHostToDevice, st));
         PF_CUDA_CHECK(cudaMemcpyAsync(converged + p, &conv, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if (sh && (rc = pf_halo_exchange(sh->halo, u, 1, st))) return rc;  // halo rows follow the owners' last step
         if (reactions_all) {
             if ((rc = materials())) return rc;
             if ((rc = pf_residual(plan, PF_ELEM_LINEAR, 1, u, E, A, 0, fint, nullptr, 0, 0.0, nullptr, nullptr, nullptr, st)))
                 return rc;
             reactions_kernel<<<db, 256, 0, st>>>(fint, f_ext, cfg->load_factor, plan->d_dof_free, ndof,
                                                  reactions_all + p * ndof);
+            if (ndof > nd_own)  // halo rows belong to the neighbours
+                PF_CUDA_CHECK(cudaMemsetAsync(reactions_all + p * ndof + nd_own, 0, (ndof - nd_own) * sizeof(double), st));
             PF_CUDA_CHECK(cudaGetLastError());
         }
         PF_CUDA_CHECK(cudaStreamSynchronize(st));  // iters / conv are stack variables
     }
     return PF_OK;
+}
+
+extern "C" int pf_gd_solve_sharded(pf_plan* plan, const pf_gd_config* cfg, const pf_gd_shard* shard, double* theta,
+                                   double* u_local, const double* f_ext_local, const int32_t* meas_dofs_local,
+                                   const double* meas_vals_local, double* history, int32_t* n_iters,
+                                   int32_t* converged, double* reactions_local, void* stream) {
+    int rc = pf_plan_activate(plan);
+    if (rc) return rc;
+    PF_REQUIRE(cfg && shard && u_local && f_ext_local && n_iters && converged, "pf_gd_solve_sharded: NULL argument");
+    PF_REQUIRE(cfg->kind == PF_ELEM_LINEAR, "pf_gd_solve_sharded supports the linear element only");
+    PF_REQUIRE(cfg->max_iterations >= 0, "max_iterations must be >= 0");
+    return pf_gd_solve_large(plan, cfg, 1, theta, u_local, f_ext_local, meas_dofs_local, meas_vals_local, history, n_iters,
+                             converged, reactions_local, pf_stream_of(stream), shard);
 }

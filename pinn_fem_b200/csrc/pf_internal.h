@@ -143,6 +143,11 @@ int pf_plan_activate(const pf_plan* plan);  // cudaSetDevice + uploaded check
 // pf_gd_large.cu: the PINN-GD loop as a device-resident sequence of kernels (large meshes)
 int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, double* theta, double* u,
                       const double* f_ext, const int32_t* meas_dofs, const double* meas_vals, double* history,
-                      int32_t* n_iters, int32_t* converged, double* reactions, cudaStream_t st);
+                      int32_t* n_iters, int32_t* converged, double* reactions, cudaStream_t st,
+                      const pf_gd_shard* shard = nullptr);
+
+// pf_comm.cu
+int pf_comm_world(const pf_comm* c);
+pf_comm* pf_halo_comm(pf_halo* h);
 
 static inline cudaStream_t pf_stream_of(void* s) { return reinterpret_cast<cudaStream_t>(s); }
