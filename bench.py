@@ -255,7 +255,18 @@ def cpu_reference_leg(steps, warmup, sample_problems=None):
             "python_loop_element_evals_per_s": py_rate, "ms_per_step": 1e3 * total / len(times)}
 
 
+def _claim_stdout():
+    """Rank 0 must print exactly ONE line on stdout.  Libraries write banners there too (NCCL prints its
+    version on the first collective), so file descriptor 1 is pointed at stderr for the duration of the run and
+    the JSON line goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
+    out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -296,7 +307,7 @@ def main():
                 "note": "reference is pure Python (no compiled code to build); this arm times the C/OpenMP "
                         "restatement of its element loop on all host threads. The literal Python loop runs at "
                         f"{base['python_loop_element_evals_per_s']:.0f} element_evals/s on one core."}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out_stream, flush=True)
         return 0
 
     import numpy as np
@@ -427,6 +438,10 @@ def main():
 
             extra["pinn_gd_large_mesh"] = gd_large_mesh_iterations_per_second(dev, plan, world)
             launches += extra["pinn_gd_large_mesh"].pop("gpu_launches", 0)
+            if world > 1:
+                from pinn_fem_b200.bench_gd import gd_element_sharded_iterations_per_second
+
+                extra["pinn_gd_element_sharded"] = gd_element_sharded_iterations_per_second(dev, nodes, el, fixed, world)
         except Exception as exc:  # the headline metric must not depend on the secondary one
             extra["pinn_gd"] = {"error": f"{type(exc).__name__}: {exc}"}
 
@@ -445,7 +460,7 @@ def main():
                 "gpu_launches": args.steps,  # timed region: exactly one patch_gather_kernel launch per step
                 "gpu_launches_all_legs": launches, "clocks": clocks}
         line.update(extra)
-        print(json.dumps(line))
+        print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -71,7 +71,7 @@ def gd_iterations_per_second(device, world=1, iters=2000, batched_problems=512, 
     return out
 
 
-def gd_large_mesh_iterations_per_second(device, plan, world=1, iters=40):
+def gd_large_mesh_iterations_per_second(device, plan, world=1, iters=100):
     """PINN-GD on the C5 lattice itself (one inverse problem per GPU, 999,941 elements): E and A are the
     521- and 316-parameter MLPs evaluated at every element centroid each iteration, the loop is the
     device-resident multi-kernel sequence of pf_gd_large.cu (MLP backward on the fp64 tensor pipe)."""
@@ -107,3 +107,49 @@ def gd_large_mesh_iterations_per_second(device, plan, world=1, iters=40):
             "dtype": "f64", "ms_per_iteration": ms / iters, "iters_per_s": world * iters / (ms * 1e-3),
             "element_evals_per_s": world * iters * plan.nelem / (ms * 1e-3),
             "gpu_launches": 2 * iters * 12}
+
+
+def gd_element_sharded_iterations_per_second(device, nodes, elements, fixed, world, iters=100):
+    """The same large-mesh PINN-GD problem as ``gd_large_mesh_iterations_per_second`` but ONE problem sharded by
+    element over all ranks (strong scaling): row bands of the lattice, halo exchange of u and r with the two
+    neighbours and one all-reduce of [dL/dtheta | losses] per iteration over NCCL/NVLink."""
+    import torch.distributed as dist
+
+    from .element_sharding import Communicator, ShardedMesh, gd_solve_element_sharded
+
+    comm = Communicator(device)
+    mesh = ShardedMesh(nodes, elements, fixed, comm)
+    nets = [ops.NetSpec(3, 2, 20), ops.NetSpec(3, 2, 15), None]
+    nnode = len(nodes)
+    g = torch.Generator(device=device).manual_seed(7)
+    f_ext = (torch.randn(2 * nnode, generator=g, device=device, dtype=torch.float64) * 1e-3).cpu().numpy()
+    theta0 = _theta0(1, device)[0, : nets[0].n_params + nets[1].n_params].contiguous()
+    md = np.arange(2 * nnode - 64, 2 * nnode, dtype=np.int64)
+    mv = np.linspace(-1e-3, 1e-3, md.size)
+    kw = dict(max_iterations=iters, tolerance=0.0, learning_rate_u=1e-5, learning_rate_theta=5e-4, alpha_physics=1.0,
+              alpha_data=100.0, load_factor=1.0)
+    u0 = np.zeros(2 * nnode)
+    best = None
+    for rep in range(2):
+        dist.barrier()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = gd_solve_element_sharded(mesh, nets, [1.0, 1.0, 1.0], theta0, u0, f_ext, md, mv, **kw)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    assert out["n_iters"] == iters
+    t = torch.tensor([best], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    res = {"workload": f"{len(elements)}-element lattice, ONE inverse problem sharded by element over {world} GPUs "
+                       f"({mesh.local.n_owned} owned + {mesh.local.halo.size} halo nodes on rank {comm.rank}), "
+                       f"{iters} iterations", "scaling": "strong", "dtype": "f64", "ms_per_iteration": ms / iters,
+           "iters_per_s": iters / (ms * 1e-3), "collectives_per_iteration": "2 halo exchanges (ncclSend/Recv group) + "
+                                                                            "1 all-reduce of 840 doubles",
+           "timed_region_includes": "host->device staging of the local vectors and the final halo exchange"}
+    mesh.close()
+    comm.close()
+    return res
