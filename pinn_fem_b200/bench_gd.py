@@ -139,15 +139,19 @@ def gd_element_sharded_iterations_per_second(device, nodes, elements, fixed, wor
         e1.record()
         torch.cuda.synchronize(device)
         ms = e0.elapsed_time(e1)
-        best = ms if best is None else min(best, ms)
+        if best is None or ms < best:
+            best, loop_ms = ms, out["solve_ms"]
     assert out["n_iters"] == iters
     t = torch.tensor([best], device=device, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    t2 = torch.tensor([loop_ms], device=device, dtype=torch.float64)
+    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     res = {"workload": f"{len(elements)}-element lattice, ONE inverse problem sharded by element over {world} GPUs "
                        f"({mesh.local.n_owned} owned + {mesh.local.halo.size} halo nodes on rank {comm.rank}), "
                        f"{iters} iterations", "scaling": "strong", "dtype": "f64", "ms_per_iteration": ms / iters,
-           "iters_per_s": iters / (ms * 1e-3), "collectives_per_iteration": "2 halo exchanges (ncclSend/Recv group) + "
+           "iters_per_s": iters / (ms * 1e-3), "loop_only_ms_per_iteration": float(t2.item()) / iters,
+           "collectives_per_iteration": "2 halo exchanges (ncclSend/Recv group) + "
                                                                             "1 all-reduce of 840 doubles",
            "timed_region_includes": "host->device staging of the local vectors and the final halo exchange"}
     mesh.close()

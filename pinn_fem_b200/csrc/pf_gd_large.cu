@@ -108,7 +108,18 @@ __global__ void __launch_bounds__(1024) adam_theta_finish_kernel(LargeCfg c, int
                                                                  const double* __restrict__ upart, int n_upart,
                                                                  double* __restrict__ sc, double* __restrict__ history) {
     __shared__ double tn[3 * 2 * (PF_MLP_MAX_LAYERS + 1)];
+    __shared__ double ured[1024];
     const bool done = sc[S_DONE] != 0.0;
+    {   // ||u_free||^2: the partial sums of adam_u_kernel, folded by a fixed tree
+        double s = 0.0;
+        for (int b = threadIdx.x; b < n_upart; b += blockDim.x) s += upart[b];
+        ured[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) ured[threadIdx.x] += ured[threadIdx.x + o];
+            __syncthreads();
+        }
+    }
     const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
     const double pb1 = sc[S_POW_B1] * b1, pb2 = sc[S_POW_B2] * b2;
     const double bc1 = 1.0 - pb1, bc2s = sqrt(1.0 - pb2);
@@ -135,8 +146,7 @@ __global__ void __launch_bounds__(1024) adam_theta_finish_kernel(LargeCfg c, int
     if (threadIdx.x == 0 && !done) {
         double tsum = 0.0;
         for (int t = 0; t < tl.n; ++t) tsum += tn[t];
-        double un = n_upart ? 0.0 : losses[L_UNORM_SQ];  // sharded runs pre-reduce ||u_free||^2 into the buffer
-        for (int b = 0; b < n_upart; ++b) un += upart[b];
+        const double un = n_upart ? ured[0] : losses[L_UNORM_SQ];  // sharded runs pre-reduce it into the buffer
         const int it = (int)sc[S_ITERS];  // 0-based index of this iteration
         const double s2 = 2.0 * losses[L_HALF_SQ];
         const double loss_p = c.legacy ? s2 / (double)c.nfree : 0.5 * s2;
@@ -186,13 +196,19 @@ __global__ void __launch_bounds__(kRedThreads) sq_partial_kernel(const double* _
     if (threadIdx.x == 0) part[blockIdx.x] = red[0];
 }
 
-// out = scale * sum(part[0..n)) in ascending order
-__global__ void sum_partials_kernel(const double* __restrict__ part, int n, double scale, double* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < n; ++i) s += part[i];
-        *out = scale * s;
+// out = scale * sum(part[0..n)): one block, strided partial sums folded by a fixed tree
+__global__ void __launch_bounds__(kRedThreads) sum_partials_kernel(const double* __restrict__ part, int n, double scale,
+                                                                   double* __restrict__ out) {
+    __shared__ double red[kRedThreads];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += kRedThreads) s += part[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *out = scale * red[0];
 }
 
 // elements on a partition interface are local to both ranks: only the owner contributes to dL/dtheta
@@ -389,7 +405,7 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
                 // halo rows of the local residual are incomplete sums: drop them, then fetch the owners' values
                 if (ndof > nd_own) PF_CUDA_CHECK(cudaMemsetAsync(r + nd_own, 0, (ndof - nd_own) * sizeof(double), st));
                 sq_partial_kernel<<<ublocks, kRedThreads, 0, st>>>(r, nd_own, upart);
-                sum_partials_kernel<<<1, 32, 0, st>>>(upart, ublocks, 0.5, losses + L_HALF_SQ);
+                sum_partials_kernel<<<1, kRedThreads, 0, st>>>(upart, ublocks, 0.5, losses + L_HALF_SQ);
                 if ((rc = pf_halo_exchange(sh->halo, r, 1, st))) return rc;
             }
             // reverse pass: dL/du = gscale K r, dL/dE, dL/dA, dL/dtheta (closed form of the autograd graph)
@@ -407,7 +423,7 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
             if (local_meas) data_loss_kernel<<<1, kRedThreads, 0, st>>>(meas_dofs, mv, n_meas, u, losses);
             adam_u_kernel<<<ublocks, kRedThreads, 0, st>>>(c, nd_own, gu, msum, mcnt, plan->d_dof_free, u, mu, vu, sc, upart);
             if (sh) {  // one all-reduce per iteration: [dL/dtheta | 0.5 sum r^2 | sum data^2 | sum u_free^2]
-                sum_partials_kernel<<<1, 32, 0, st>>>(upart, ublocks, 1.0, losses + L_UNORM_SQ);
+                sum_partials_kernel<<<1, kRedThreads, 0, st>>>(upart, ublocks, 1.0, losses + L_UNORM_SQ);
                 if ((rc = pf_comm_allreduce_sum(comm, gt, ntheta + L_COUNT, st))) return rc;
             }
             adam_theta_finish_kernel<<<1, 1024, 0, st>>>(c, n_active, ntheta, tl, gt, theta, mt, vt, losses, upart,

@@ -239,13 +239,22 @@ __global__ void __launch_bounds__(PTS) mlp_backward_kernel(PfMlpDesc d, const do
     }
 }
 
-__global__ void reduce_rows_kernel(const double* __restrict__ part, int64_t rows, int64_t cols,
-                                   double* __restrict__ out) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// out[c] = sum over rows of part[r][c]: a CTA per 32 columns, 32 strided partial sums per column folded
+// in a fixed order (rows = CTAs of the gradient kernel)
+__global__ void __launch_bounds__(1024) reduce_rows_kernel(const double* __restrict__ part, int64_t rows, int64_t cols,
+                                                           double* __restrict__ out) {
+    __shared__ double s[32][33];
+    const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
     double acc = 0.0;
-    for (int64_t r = 0; r < rows; ++r) acc += part[r * cols + c];
-    out[c] = acc;
+    if (c < cols)
+        for (int64_t r = threadIdx.y; r < rows; r += 32) acc += part[r * cols + c];
+    s[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        double t = 0.0;
+        for (int y = 0; y < 32; ++y) t += s[y][threadIdx.x];
+        out[c] = t;
+    }
 }
 
 }  // namespace
@@ -431,7 +440,7 @@ extern "C" int pf_mlp_backward(pf_plan* plan, int input_dim, int hidden_layers, 
             rc = pf_mlp_tc_launch(d, true, theta, n, X, cen, load_factor, scale, enforce_positive, g_out, nullptr,
                                   tpart, grid, st);
             if (rc) return rc;
-            reduce_rows_kernel<<<(d.n_params + 127) / 128, 128, 0, st>>>(tpart, grid, d.n_params, g_theta);
+            reduce_rows_kernel<<<(d.n_params + 31) / 32, dim3(32, 32), 0, st>>>(tpart, grid, d.n_params, g_theta);
             PF_CUDA_CHECK(cudaGetLastError());
             return PF_OK;
         }
@@ -452,7 +461,7 @@ extern "C" int pf_mlp_backward(pf_plan* plan, int input_dim, int hidden_layers, 
 #undef PF_BWD
     PF_CUDA_CHECK(cudaGetLastError());
     if (blocks > 1) {
-        reduce_rows_kernel<<<(d.n_params + 127) / 128, 128, 0, st>>>(part, blocks, d.n_params, g_theta);
+        reduce_rows_kernel<<<(d.n_params + 31) / 32, dim3(32, 32), 0, st>>>(part, blocks, d.n_params, g_theta);
         PF_CUDA_CHECK(cudaGetLastError());
     }
     return PF_OK;

@@ -295,11 +295,15 @@ def gd_solve_element_sharded(mesh: ShardedMesh, nets, scales, theta, u_global, f
     converged = torch.zeros(1, dtype=torch.int32, device=dev)
     reactions = torch.zeros(plan.ndof, dtype=torch.float64, device=dev)
     p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.device(dev):
+        e0.record()
         _lib.check(mesh._lib.pf_gd_solve_sharded(plan._handle, C.byref(cfg), C.byref(shard), p(theta_d), p(u), p(f_ext),
                                                  p(md_l), p(mv_l), p(history), p(n_iters), p(converged), p(reactions),
                                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        e1.record()
     n = int(n_iters[0])
     return {"u_owned": u[: mesh.n_owned_dofs], "u_local": u, "reactions_owned": reactions[: mesh.n_owned_dofs],
             "owned_dofs": lm.local_dofs_global()[: mesh.n_owned_dofs], "theta": theta_d,
-            "history": history[:n] if history is not None else None, "n_iters": n, "converged": bool(converged[0])}
+            "history": history[:n] if history is not None else None, "n_iters": n, "converged": bool(converged[0]),
+            "solve_ms": e0.elapsed_time(e1)}  # device time of the loop itself (staging of the local vectors excluded)
