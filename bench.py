@@ -255,6 +255,30 @@ def cpu_reference_leg(steps, warmup, sample_problems=None):
             "python_loop_element_evals_per_s": py_rate, "ms_per_step": 1e3 * total / len(times)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, before any pinned host buffer is
+    allocated: the end-to-end leg is a host-memory -> PCIe stream and crossing sockets halves it."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return None
+
+
 def _claim_stdout():
     """Rank 0 must print exactly ONE line on stdout.  Libraries write banners there too (NCCL prints its
     version on the first collective), so file descriptor 1 is pointed at stderr for the duration of the run and
@@ -322,6 +346,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: pinn_fem_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -404,7 +429,7 @@ def main():
            "h2d_bytes_per_step": (plan.ndof + 2 * plan.nelem) * Be * 8 + plan.ndof * 8,
            "d2h_bytes_per_step": plan.ndof * Be * 8, "problems_per_gpu": Be, "steps": e2e_steps,
            "api": "AssemblyPlan.residual_host -> pf_residual_host (pinned host buffers, chunked H2D/compute/D2H "
-                  "pipeline on 3 streams)", "matches_device_result": e2e_ok}
+                  "pipeline on 3 streams)", "matches_device_result": e2e_ok, "numa_binding": numa}
     launches = args.steps + e2e_steps * ((Be + 127) // 128)
 
     extra = {}
