@@ -150,7 +150,7 @@ def tangent_leg(plan, E, A, dev, Bt, steps, peak):
                          "algorithmic_bytes_per_launch": ab}, "gpu_launches": steps + 3}
 
 
-def jtj_leg(dev, n, m, peak_note="fp64 tensor (DMMA); B200 datasheet 40 TFLOP/s, not in MEASURED_PEAKS.json"):
+def jtj_leg(dev, n, m, peak_note="fp64 peaks are not in MEASURED_PEAKS.json: measured in this run with register-resident DFMA / DMMA loops"):
     """Secondary line: Gauss-Newton normal equations J^T J + damping (fem/nn_solver.py:268-274) on a random
     full-rank J ~ N(0,1) (SURVEY 8d, C4 scaled variant) and the LU solve of the damped system."""
     import torch
@@ -174,6 +174,7 @@ def jtj_leg(dev, n, m, peak_note="fp64 tensor (DMMA); B200 datasheet 40 TFLOP/s,
         out["jtj_ms"] = ms
         out["jtj_tflops_full_2mn2"] = 2.0 * m * n * n / (ms * 1e-3) / 1e12
         out["jtj_tflops_executed"] = out["jtj_tflops_full_2mn2"] * (n / 64 + 1) / (2 * (n / 64))  # upper tiles only
+    ops.solve_dense(jtj[:256, :256].contiguous(), -jtr[:256])  # warm-up: module load, allocator pool
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     dx = ops.solve_dense(jtj, -jtr)
@@ -181,6 +182,19 @@ def jtj_leg(dev, n, m, peak_note="fp64 tensor (DMMA); B200 datasheet 40 TFLOP/s,
     torch.cuda.synchronize(dev)
     out["lu_solve_ms"] = e0.elapsed_time(e1)
     out["lu_tflops"] = (2.0 / 3.0) * n ** 3 / (out["lu_solve_ms"] * 1e-3) / 1e12
+    import ctypes
+
+    from pinn_fem_b200 import _lib
+
+    peaks = {}
+    for kind, name in ((0, "dfma_tflops"), (1, "dmma_tflops")):
+        v = ctypes.c_double(0.0)
+        _lib.check(_lib.load().pf_measure_fp64_peak(kind, ctypes.byref(v)))
+        peaks[name] = v.value
+    out["fp64_peaks_measured"] = peaks
+    out["roofline"] = {"bound": "tensor", "achieved": out["jtj_tflops_executed"], "peak": peaks["dmma_tflops"],
+                       "unit": "TFLOP/s", "frac": out["jtj_tflops_executed"] / peaks["dmma_tflops"],
+                       "peak_source": "pf_measure_fp64_peak(DMMA) in this run"}
     out["peak_note"] = peak_note
     out["gpu_launches"] = 4 * 3 + 4 * (n // 32 + 1)
     return out

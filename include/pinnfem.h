@@ -306,6 +306,11 @@ int pf_gn_jacobian(pf_plan* plan, int kind, const double* u, const double* E, co
                    double alpha_physics, double alpha_data, const int32_t* meas_dofs, int64_t n_meas, double* J,
                    void* stream);
 
+/* fp64 peak probe for the rooflines of the compute-bound kernels (not on any solver path):
+ * kind 0 = DFMA pipe, 1 = DMMA (fp64 tensor pipe); *tflops_out (host) = measured TFLOP/s on the
+ * current device.  Synchronous, takes a few milliseconds. */
+int pf_measure_fp64_peak(int kind, double* tflops_out);
+
 /* ------------------------------------------------------------------------
  * Host-buffer convenience entry point (the end-to-end path): residual of B
  * problems whose u/E/A live in (pinned) host memory, streamed through the
