@@ -29,8 +29,14 @@ struct NetDev {
     int act_off;     // smem offset (doubles) of activations: layer 0 [nelem][in], layers 1..L [nelem][w]
     int val_off;     // smem: value per element; +nelem: d value / dz per element
     double scale;
+    unsigned div_w, div_in;  // magic multipliers: x / w and x / in_dim for x < 65536 (see fast_div)
     PfMlpDesc d;
 };
+
+// x / d for x < 2^16 and d < 256 with m = ceil(2^24 / d): the error x (m - 2^24/d) / 2^24 stays below 2^-8,
+// less than the gap (1/d) between frac(x/d) and the next integer.  A runtime integer division costs ~25
+// instructions in every item loop of this latency-bound kernel.
+__device__ __forceinline__ int fast_div(int x, unsigned m) { return (int)__umulhi((unsigned)x << 8, m); }
 
 struct GdArgs {
     // mesh
@@ -135,7 +141,7 @@ __device__ __forceinline__ void forward_hidden(const GdArgs& a, double* sm, int 
     for (int q = threadIdx.x; q < c0 + c1; q += blockDim.x) {
         const NetDev& n = q < c0 ? n0 : n1;
         const int qq = q < c0 ? q : q - c0;
-        const int e = qq / n.d.w, o = qq - e * n.d.w;
+        const int e = fast_div(qq, n.div_w), o = qq - e * n.d.w;
         const int in = l == 0 ? n.d.in_dim : n.d.w;
         const double* th = sm + a.o_theta + n.theta_off;
         const double z = th[n.d.b_off[l] + o] + dot4(th + n.d.w_off[l] + o * in, 1, act_ptr(a, n, sm, l) + e * in, 1, in);
@@ -266,6 +272,22 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
     if (tid == 0) red[5] = 0.0;
     __syncthreads();
 
+    // parameter tensors in nn.Module.parameters() order: offset and size of each (monitoring norms)
+    __shared__ int s_toff[3 * 2 * (PF_MLP_MAX_LAYERS + 1)], s_tcnt[3 * 2 * (PF_MLP_MAX_LAYERS + 1)];
+    if (tid == 0) {
+        int tix = 0;
+        for (int k = 0; k < kMaxNets; ++k) {
+            const NetDev& n = a.nets[k];
+            if (!n.enabled) continue;
+            for (int l = 0; l <= n.d.L; ++l) {
+                const int in = l == 0 ? n.d.in_dim : n.d.w;
+                s_toff[tix] = n.theta_off + n.d.w_off[l];
+                s_tcnt[tix++] = l == n.d.L ? n.d.w : n.d.w * in;
+                s_toff[tix] = n.theta_off + n.d.b_off[l];
+                s_tcnt[tix++] = l == n.d.L ? 1 : n.d.w;
+            }
+        }
+    }
     int maxL = 0;
     for (int k = 0; k < 2; ++k)
         if (a.nets[k].enabled) maxL = max(maxL, a.nets[k].d.L);
@@ -386,7 +408,7 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
                     g[n.d.b_off[L]] = acc;
                 } else {
                     qq -= w + 1;
-                    const int e = qq / w, o = qq - e * w;
+                    const int e = fast_div(qq, n.div_w), o = qq - e * w;
                     const double av = aL[qq];
                     (sm + a.o_delta + k * 2 * a.nelem * a.wmax)[qq] = th[n.theta_off + n.d.w_off[L] + o] * dz[e] * (1.0 - av * av);
                 }
@@ -412,7 +434,7 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
                     const double* ain = act_ptr(a, n, sm, l);
                     double* g = sm + a.o_g + n.theta_off;
                     if (qq < w * in) {
-                        const int o = qq / in, i = qq - o * in;
+                        const int o = fast_div(qq, l == 0 ? n.div_in : n.div_w), i = qq - o * in;
                         g[n.d.w_off[l] + qq] = dot4(D + o, w, ain + i, in, a.nelem);
                     } else if (qq < w * in + w) {
                         const int o = qq - w * in;
@@ -421,7 +443,7 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
                         g[n.d.b_off[l] + o] = acc;
                     } else {
                         qq -= w * in + w;
-                        const int e = qq / w, i = qq - e * w;
+                        const int e = fast_div(qq, n.div_w), i = qq - e * w;
                         const double av = ain[qq];
                         Dn[qq] = dot4(th + n.theta_off + n.d.w_off[l] + i, w, D + e * w, 1, w) * (1.0 - av * av);
                     }
@@ -457,25 +479,15 @@ __global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
         // ---- monitoring (solver.py:304-322): ||u_free||, per-tensor parameter norms; read by thread 0
         //      at the top of the next iteration ----
         {
-            int tix = 0;
-            for (int k = 0; k < kMaxNets; ++k) {
-                const NetDev& n = a.nets[k];
-                if (!n.enabled) continue;
-                for (int l = 0; l <= n.d.L; ++l) {
-                    for (int wb = 0; wb < 2; ++wb, ++tix) {
-                        if (tix % nwarp != warp) continue;
-                        const int off = n.theta_off + (wb == 0 ? n.d.w_off[l] : n.d.b_off[l]);
-                        const int in = l == 0 ? n.d.in_dim : n.d.w;
-                        const int cnt = wb == 0 ? (l == n.d.L ? n.d.w : n.d.w * in) : (l == n.d.L ? 1 : n.d.w);
-                        double s0 = 0.0, s1 = 0.0;
-                        for (int i = lane; i < cnt; i += 64) {
-                            s0 = fma(th[off + i], th[off + i], s0);
-                            if (i + 32 < cnt) s1 = fma(th[off + i + 32], th[off + i + 32], s1);
-                        }
-                        const double s = warp_sum(s0 + s1);
-                        if (lane == 0) sm[a.o_tn + tix] = sqrt(s);
-                    }
+            for (int tix = warp; tix < a.n_tensors; tix += nwarp) {  // tensor table built once before the loop
+                const int off = s_toff[tix], cnt = s_tcnt[tix];
+                double s0 = 0.0, s1 = 0.0;
+                for (int i = lane; i < cnt; i += 64) {
+                    s0 = fma(th[off + i], th[off + i], s0);
+                    if (i + 32 < cnt) s1 = fma(th[off + i + 32], th[off + i + 32], s1);
                 }
+                const double s = warp_sum(s0 + s1);
+                if (lane == 0) sm[a.o_tn + tix] = sqrt(s);
             }
             if (warp == nwarp - 1) {
                 double s = 0.0;
@@ -565,6 +577,8 @@ extern "C" int pf_gd_solve(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob
             PF_REQUIRE(n.d.in_dim == plan->dim + 1,
                        "network input_dim %d does not match [load_factor, centroid] = %d inputs "
                        "(fem/properties.py:116-125)", n.d.in_dim, plan->dim + 1);
+            n.div_w = ((1u << 24) + n.d.w - 1) / n.d.w;
+            n.div_in = ((1u << 24) + n.d.in_dim - 1) / n.d.in_dim;
             ntheta += n.d.n_params;
             ntens += 2 * (n.d.L + 1);
             max_w = std::max(max_w, n.d.w);
@@ -605,7 +619,7 @@ extern "C" int pf_gd_solve(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob
     }
     a.smem_doubles = off;
     const size_t smem = (size_t)off * sizeof(double);
-    if (smem > 200 * 1024)  // does not fit one CTA: the multi-kernel device-resident loop (pf_gd_large.cu)
+    if (smem > 200 * 1024 || (int64_t)a.nelem * max_w >= 65536)  // does not fit one CTA (fast_div range: items < 2^16): the multi-kernel device-resident loop (pf_gd_large.cu)
         return pf_gd_solve_large(plan, cfg, nprob, theta, u, f_ext, meas_dofs, meas_vals, history, n_iters, converged,
                                  reactions, pf_stream_of(stream), nullptr);
     if (smem > 48 * 1024)
