@@ -13,6 +13,7 @@
 // bitwise reproducible.  Meshes/networks that do not fit the shared-memory
 // budget run the same iteration as a sequence of kernels (pf_gd_large.cu).
 #include <algorithm>
+#include <cstdlib>
 
 #include "pf_element.cuh"
 #include "pf_internal.h"
@@ -193,7 +194,7 @@ __device__ __forceinline__ void gather_linear(const GdArgs& a, const MeshS& ms, 
     }
 }
 
-__global__ void __launch_bounds__(256) gd_solve_kernel(GdArgs a) {
+__global__ void __launch_bounds__(1024) gd_solve_kernel(GdArgs a) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     const int64_t prob = blockIdx.x;
@@ -625,7 +626,14 @@ extern "C" int pf_gd_solve(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob
     if (smem > 48 * 1024)
         PF_CUDA_CHECK(cudaFuncSetAttribute(gd_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int work = std::max({a.nelem * max_w, a.ndof, max_w * max_w + max_w, 32});
-    const int threads = work <= 64 ? 64 : work <= 128 ? 128 : 256;
+    int threads = work <= 64 ? 64 : work <= 128 ? 128 : 256;
+    // few problems: the SMs are mostly idle and each phase is a dependent fp64 chain per item (tanh, sqrt,
+    // division), so more threads = fewer items per thread = shorter phases (10.4 vs 12.6 us per iteration at
+    // one problem); many problems: 256-thread CTAs keep more problems resident per SM (30.8 vs 12.1 M it/s).
+    if (work > 256 && nprob <= plan->sm_count) threads = 1024;
+    else if (work > 256 && nprob <= 2 * (int64_t)plan->sm_count) threads = 512;
+    static const int env_threads = getenv("PF_GD_THREADS") ? atoi(getenv("PF_GD_THREADS")) : 0;
+    if (env_threads >= 32 && env_threads <= 1024 && env_threads % 32 == 0) threads = env_threads;
     gd_solve_kernel<<<(unsigned)nprob, threads, smem, pf_stream_of(stream)>>>(a);
     PF_CUDA_CHECK(cudaGetLastError());
     return PF_OK;
