@@ -174,7 +174,8 @@ def jtj_leg(dev, n, m, peak_note="fp64 peaks are not in MEASURED_PEAKS.json: mea
         out["jtj_ms"] = ms
         out["jtj_tflops_full_2mn2"] = 2.0 * m * n * n / (ms * 1e-3) / 1e12
         out["jtj_tflops_executed"] = out["jtj_tflops_full_2mn2"] * (n / 64 + 1) / (2 * (n / 64))  # upper tiles only
-    ops.solve_dense(jtj[:256, :256].contiguous(), -jtr[:256])  # warm-up: module load, allocator pool
+    for _ in range(2):  # warm-up at full size: module load, allocator pools
+        ops.solve_dense(jtj, -jtr)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     dx = ops.solve_dense(jtj, -jtr)

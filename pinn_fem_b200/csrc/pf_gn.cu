@@ -15,10 +15,11 @@ namespace {
 
 // ---------------------------------------------------------------------------------------
 // J^T J with mma.sync.aligned.m8n8k4.f64 (DMMA).  CTA tile 64x64 of C, 4 warps of 32x32,
-// K (rows of J) consumed 16 at a time from shared memory.  Only tiles with j0 >= i0 are
-// computed; the mirror tile is written from the same accumulators.
+// K (rows of J) consumed 32 at a time from a double-buffered shared-memory stage.  Only tiles
+// with j0 >= i0 are computed; the mirror tile is written from the same accumulators.
 // ---------------------------------------------------------------------------------------
-constexpr int TN = 64, KC = 16, LDS_ = TN + 4;  // row stride 68 doubles: conflict-free fragment loads
+constexpr int TN = 64, KC = 32, LDS_ = TN + 4;  // row stride 68 doubles: conflict-free fragment loads
+constexpr int kJtjStage = 2 * KC * LDS_;         // doubles per pipeline stage (I tile + J tile)
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -26,12 +27,14 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
+// Two-stage cp.async pipeline over the rows of J: while the warps run the 8 k4-steps (128 DMMA each) of
+// chunk c, the 2 x 32 x 64 doubles of chunk c+1 stream into the other stage.  Edge tiles (ragged n or m,
+// odd n: 16-byte alignment) take synchronous zero-filled loads instead.
 __global__ void __launch_bounds__(128) jtj_dmma_kernel(int64_t m, int64_t n, const double* __restrict__ J,
                                                        double* __restrict__ C) {
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bj < bi) return;  // symmetric: upper tiles only
-    __shared__ double sI[KC][LDS_];
-    __shared__ double sJ[KC][LDS_];
+    extern __shared__ __align__(16) double jsm[];
     const int64_t i0 = (int64_t)bi * TN, j0 = (int64_t)bj * TN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wi = (warp >> 1) * 32, wj = (warp & 1) * 32;  // warp's 32x32 corner inside the tile
@@ -42,27 +45,59 @@ __global__ void __launch_bounds__(128) jtj_dmma_kernel(int64_t m, int64_t n, con
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    for (int64_t r0 = 0; r0 < m; r0 += KC) {
-        for (int q = tid; q < KC * TN; q += 128) {
-            const int k = q / TN, c = q % TN;
-            const int64_t r = r0 + k;
-            sI[k][c] = (r < m && i0 + c < n) ? J[r * n + i0 + c] : 0.0;
-            sJ[k][c] = (r < m && j0 + c < n) ? J[r * n + j0 + c] : 0.0;
+    const bool interior = i0 + TN <= n && j0 + TN <= n && (n & 1) == 0 &&
+                          (reinterpret_cast<uintptr_t>(J) & 15) == 0;
+    auto load = [&](int64_t r0, int stage) {
+        double* sI = jsm + stage * kJtjStage;
+        double* sJ = sI + KC * LDS_;
+        if (interior && r0 + KC <= m) {
+            // 2 tiles x 32 rows x 32 16-byte pieces = 2048 copies, 16 per thread
+            for (int q = tid; q < 2 * KC * (TN / 2); q += 128) {
+                const int which = q / (KC * (TN / 2)), rem = q - which * (KC * (TN / 2));
+                const int k = rem / (TN / 2), c2 = rem - k * (TN / 2);
+                const double* src = J + (r0 + k) * n + (which ? j0 : i0) + 2 * c2;
+                double* dst = (which ? sJ : sI) + k * LDS_ + 2 * c2;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                             "l"(src)
+                             : "memory");
+            }
+        } else {
+            for (int q = tid; q < KC * TN; q += 128) {
+                const int k = q / TN, c = q % TN;
+                const int64_t r = r0 + k;
+                sI[k * LDS_ + c] = (r < m && i0 + c < n) ? J[r * n + i0 + c] : 0.0;
+                sJ[k * LDS_ + c] = (r < m && j0 + c < n) ? J[r * n + j0 + c] : 0.0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int64_t nchunk = (m + KC - 1) / KC;
+    load(0, 0);
+    for (int64_t c = 0; c < nchunk; ++c) {
+        const int stage = (int)(c & 1);
+        if (c + 1 < nchunk) {
+            load((c + 1) * KC, stage ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        const double* sI = jsm + stage * kJtjStage;
+        const double* sJ = sI + KC * LDS_;
 #pragma unroll
         for (int k4 = 0; k4 < KC; k4 += 4) {
             double af[4], bf[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) af[a] = sI[k4 + t][wi + a * 8 + g];  // A[row g][k t] = J[k][i]
+            for (int a = 0; a < 4; ++a) af[a] = sI[(k4 + t) * LDS_ + wi + a * 8 + g];  // A[row g][k t] = J[k][i]
 #pragma unroll
-            for (int b = 0; b < 4; ++b) bf[b] = sJ[k4 + t][wj + b * 8 + g];  // B[k t][col g] = J[k][j]
+            for (int b = 0; b < 4; ++b) bf[b] = sJ[(k4 + t) * LDS_ + wj + b * 8 + g];  // B[k t][col g] = J[k][j]
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
         }
-        __syncthreads();
+        __syncthreads();  // the stage is refilled by the next iteration's load
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -180,7 +215,9 @@ extern "C" int pf_gn_normal_equations(int64_t m, int64_t n, const double* J, con
     PF_REQUIRE(J && jtj, "pf_gn_normal_equations: NULL argument");
     cudaStream_t st = pf_stream_of(stream);
     const unsigned tiles = (unsigned)((n + TN - 1) / TN);
-    jtj_dmma_kernel<<<dim3(tiles, tiles), 128, 0, st>>>(m, n, J, jtj);
+    constexpr size_t kJtjSmem = 2 * kJtjStage * sizeof(double);
+    PF_CUDA_CHECK(cudaFuncSetAttribute(jtj_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJtjSmem));
+    jtj_dmma_kernel<<<dim3(tiles, tiles), 128, kJtjSmem, st>>>(m, n, J, jtj);
     PF_CUDA_CHECK(cudaGetLastError());
     if (R && jtr) {
         jtr_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m, n, J, R, jtr);
