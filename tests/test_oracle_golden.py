@@ -379,3 +379,22 @@ def test_c_oracle_matches_numpy_oracle(assembly_golden):
         r_ref = np.zeros_like(f_ref)
         r_ref[c["free"]] = f_ref[c["free"]] - 0.3 * fx[c["free"]][:, None]
         assert rel(r, r_ref) < 1e-13
+
+
+def test_green_lagrange_element_is_kept_verbatim_including_its_sign():
+    """fem/element.py:105-133 returns fe = +EA/l0*e*d on node i (towards node j for a stretched bar) while its
+    ke is positive definite: fe has the opposite sign of dU/du, so Newton on this element cannot converge --
+    presumably why no reference solver calls it.  The port keeps it verbatim (element-level
+    goldens above); this test pins the behaviour so that nobody "fixes" one side only."""
+    xi, xj = np.array([0.0, 0.0]), np.array([1.0, 0.0])
+    ui, uj = np.zeros(2), np.array([1e-3, 0.0])  # stretched
+    ke_l, fe_l, _ = O.truss2d_linear_element(xi, xj, ui, uj, 1.0, 1.0)
+    ke_g, fe_g, e_g = O.truss2d_element_state(xi, xj, ui, uj, 1.0, 1.0)
+    assert fe_l[0] < 0 < fe_l[2]          # linear: internal force resists the stretch
+    assert fe_g[0] > 0 > fe_g[2]          # Green-Lagrange (verbatim): opposite sign
+    assert abs(abs(fe_g[0]) - abs(fe_l[0])) < 2e-6 and e_g > 0
+    assert np.all(np.linalg.eigvalsh(ke_g) > -1e-12)
+    # finite-difference tangent of the verbatim fe is -ke (to first order in the strain)
+    h = 1e-7
+    col = (O.truss2d_element_state(xi, xj, ui + np.array([h, 0]), uj, 1.0, 1.0)[1] - fe_g) / h
+    assert np.allclose(col, -ke_g[:, 0], atol=5e-3)
