@@ -248,6 +248,41 @@ def test_example4p_whole_run_against_reference(tmp_path, example_inputs, runs):
     assert np.allclose(EA, 1.0, atol=5e-3)
 
 
+@pytest.mark.parametrize("name", ["example4-P", "example3-P"])
+def test_extract_nn_properties_matches_reference_output(tmp_path, example_inputs, runs, name):
+    """Post-processing (examples/json/generic.py:498-799): load the reference run's final nn_parameters into
+    our networks and compare the identified property fields at nodes and centroids for every load factor
+    with what the reference wrote (fp32 on its side: 1e-6)."""
+    from pinn_fem_b200.examples.json import generic
+
+    ref = runs[name]["output"]
+    p = _write(tmp_path, example_inputs[name], "problem.json")
+    torch.manual_seed(0)
+    model = generic.parse_problem(str(p))["model"]
+    params = model.material.get_all_torch_params()
+    assert len(params) == len(ref["nn_parameters"])
+    with torch.no_grad():
+        for i, prm in enumerate(params):
+            prm.copy_(torch.as_tensor(np.asarray(ref["nn_parameters"][f"param_{i}"], dtype=np.float64)).reshape(prm.shape))
+    got = generic.extract_nn_properties(model)
+    assert set(got) == set(ref["identified_properties"])
+
+    def cmp(a, b, path):
+        assert type(a) is type(b) or isinstance(a, (int, float)) and isinstance(b, (int, float)), path
+        if isinstance(a, dict):
+            assert set(a) == set(b), path
+            for k in a:
+                cmp(a[k], b[k], path + "/" + k)
+        elif isinstance(a, list):
+            assert np.allclose(np.asarray(a, dtype=float), np.asarray(b, dtype=float), rtol=2e-6, atol=1e-9), path
+        elif isinstance(a, (int, float)) and not isinstance(a, bool):
+            assert abs(a - b) <= 2e-6 * max(1.0, abs(b)), path
+        else:
+            assert a == b, path
+
+    cmp(got, ref["identified_properties"], name)
+
+
 def test_solve_gd_matches_oracle_end_state(tmp_path, example_inputs):
     """fem.solver.solve (method gd, 3 increments, preconditioning) vs the fp64 oracle driver from the
     same theta_0: final u and identified E, A agree to 1e-8 (north star)."""
