@@ -445,7 +445,7 @@ def main():
            "d2h_bytes_per_step": plan.ndof * Be * 8, "problems_per_gpu": Be, "steps": e2e_steps,
            "api": "AssemblyPlan.residual_host -> pf_residual_host (pinned host buffers, chunked H2D/compute/D2H "
                   "pipeline on 3 streams)", "matches_device_result": e2e_ok, "numa_binding": numa}
-    launches = args.steps + e2e_steps * ((Be + 127) // 128)
+    launches = args.steps + e2e_steps * ((Be + 63) // 64)
 
     extra = {}
     if not args.no_tangent:

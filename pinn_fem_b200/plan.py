@@ -257,7 +257,7 @@ class AssemblyPlan:
         return self.bsr_to_dense(self.tangent_bsr(E, A, u, kind), free_only)
 
     def residual_host(self, u_host, E_host, A_host, f_ext_host, load_factor=1.0, r_host=None, kind="linear",
-                      chunk: int = 128):
+                      chunk: int = 64):
         """End-to-end call on HOST tensors ``[rows, B]`` (pinned for full speed):
         chunks are copied in, evaluated and copied back on overlapping streams."""
         self._need_device()
