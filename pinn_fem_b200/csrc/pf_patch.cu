@@ -365,7 +365,7 @@ int pf_patch_gather(pf_plan* plan, const PfGatherCall& c, cudaStream_t st, int64
     const size_t smem = ch == 16 ? smem16 : smem32;
     if (smem > 225 * 1024) return PF_OK;
     const int64_t ncol = (c.B / ch) * ch;  // full chunks only; the tail goes to the generic kernel
-    if (ncol < 128) return PF_OK;          // too few chunks to pipeline: generic kernel
+    if (ncol < 4 * ch) return PF_OK;       // too few chunks to pipeline: generic kernel
 
     PatchArgs a{};
     a.patches = plan->d_patches;
