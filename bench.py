@@ -450,9 +450,9 @@ def main():
     extra = {}
     if not args.no_tangent:
         try:
-            extra["tangent_bsr"] = tangent_leg(plan, E, A, dev, min(B, 16), max(3, min(args.steps, 10)), peak)
+            extra["tangent_bsr"] = tangent_leg(plan, E, A, dev, min(B, 64), max(3, min(args.steps, 10)), peak)
             t_ms = max_over_ranks(extra["tangent_bsr"]["ms_per_launch"], dev)
-            extra["tangent_bsr"]["element_evals_per_s"] = world * min(B, 16) * plan.nelem / (t_ms * 1e-3)
+            extra["tangent_bsr"]["element_evals_per_s"] = world * min(B, 64) * plan.nelem / (t_ms * 1e-3)
             launches += extra["tangent_bsr"].pop("gpu_launches")
         except Exception as exc:
             extra["tangent_bsr"] = {"error": f"{type(exc).__name__}: {exc}"}
