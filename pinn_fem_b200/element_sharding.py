@@ -82,6 +82,8 @@ def partition_mesh(nodes, elements, fixed_dofs, world: int, part: Optional[np.nd
     part = contiguous_node_partition(nnode, world) if part is None else np.asarray(part, dtype=np.int32)
     if part.shape != (nnode,) or part.min() < 0 or part.max() >= world:
         raise ValueError("part must assign every node a rank in [0, world)")
+    if np.bincount(part, minlength=world).min() == 0:
+        raise ValueError(f"every rank must own at least one node ({nnode} nodes over {world} ranks)")
     fixed = np.unique(np.asarray(fixed_dofs, dtype=np.int64))
     ndof = nnode * dim
     nfree_global = ndof - fixed.size

@@ -80,3 +80,7 @@ def test_bad_partition_is_rejected():
     nodes, el, fixed = lattice_truss(4)
     with pytest.raises(ValueError):
         partition_mesh(nodes, el, fixed, 2, part=np.full(len(nodes), 2, dtype=np.int32))
+    with pytest.raises(ValueError):  # a rank without nodes
+        partition_mesh(nodes, el, fixed, 2, part=np.zeros(len(nodes), dtype=np.int32))
+    with pytest.raises(ValueError):
+        partition_mesh(nodes[:3], el[:0], [], 4)
