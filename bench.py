@@ -478,6 +478,10 @@ def main():
 
             extra["pinn_gd_large_mesh"] = gd_large_mesh_iterations_per_second(dev, plan, world)
             launches += extra["pinn_gd_large_mesh"].pop("gpu_launches", 0)
+            if rank == 0:
+                from pinn_fem_b200.bench_gd import example_runs
+
+                extra["examples"] = example_runs(ROOT / "tests" / "golden" / "inputs")
             if world > 1:
                 from pinn_fem_b200.bench_gd import gd_element_sharded_iterations_per_second
 

@@ -157,3 +157,51 @@ def gd_element_sharded_iterations_per_second(device, nodes, elements, fixed, wor
     mesh.close()
     comm.close()
     return res
+
+
+def example_runs(golden_inputs_dir, names=("example1", "example4-P", "example7-P")):
+    """BASELINE.json configs[0..2]: whole ``generic.py`` solves (parse + solve + post-processing, seed 0) of the
+    reference's own example files, timed warm (second run) on the wall clock, next to the reference's timings
+    recorded in BASELINE.md (CPU)."""
+    import io
+    import json
+    import time
+    from contextlib import redirect_stdout
+    from pathlib import Path
+    import logging
+    import tempfile
+
+    from .examples.json import generic
+    from .fem import solver
+
+    ref = {"example1": {"wall_s": 7.5, "note": "BASELINE.md: 7.5 s here, ~all interpreter start-up; README ~1 s"},
+           "example4-P": {"wall_s": 33.8, "iterations": 1874, "iters_per_s": 55.0},
+           "example7-P": {"wall_s": 39.7, "iterations": 2140, "iters_per_s": 54.0}}
+    out = {}
+    logging.disable(logging.CRITICAL)
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            for name in names:
+                src = Path(golden_inputs_dir) / f"{name}.json"
+                if not src.exists():
+                    continue
+                dst = Path(tmp) / src.name
+                dst.write_text(src.read_text())
+                best = None
+                for rep in range(2):
+                    torch.manual_seed(0)
+                    solver.COUNTERS["gd_iterations"] = 0
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    with redirect_stdout(io.StringIO()):
+                        res = generic.solve_problem(generic.parse_problem(str(dst)))
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+                total = solver.COUNTERS["gd_iterations"]  # GD iterations over all increments and phases
+                out[name] = {"wall_s": best, "converged": bool(res["converged"]),
+                             "result_iterations": res["iterations"], "gd_iterations_total": total,
+                             "gd_iters_per_s": (total / best) if total else None, "reference_cpu": ref.get(name)}
+    finally:
+        logging.disable(logging.NOTSET)
+    return out

@@ -62,6 +62,11 @@ def _nn_parameter_dict(model):
 # ---------------------------------------------------------------------------------------
 
 
+# running totals over all phases / increments of a process (the result object only carries the last
+# increment's history, like the reference); read by bench.py to report iterations per second
+COUNTERS = {"gd_iterations": 0, "gd_calls": 0}
+
+
 def _run_gd(model, loads, measured_disp, measured_dofs, u_initial, *, max_iterations, tolerance, learning_rate_u,
             learning_rate_theta, alpha_physics, alpha_data, load_factor, legacy_loss=False):
     """One ``solve_gd`` inner loop on the device; mutates the model's networks like the reference."""
@@ -88,6 +93,8 @@ def _run_gd(model, loads, measured_disp, measured_dofs, u_initial, *, max_iterat
     # multi-kernel loop of pf_gd_large.cu -- chosen inside pf_gd_solve
     res = ops.gd_solve(plan, nets, scales, theta if theta.numel() else None, u, f_ext, md, mv, **kw)
     n = int(res.n_iters[0])
+    COUNTERS["gd_iterations"] += n
+    COUNTERS["gd_calls"] += 1
     H = res.history[0, :n].cpu().numpy()
     converged = bool(res.converged[0])
     reactions = res.reactions[0]
