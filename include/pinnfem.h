@@ -169,6 +169,9 @@ int pf_mlp_forward(pf_plan* plan, int input_dim, int hidden_layers, int width, c
 int pf_mlp_backward(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta, int64_t n,
                     const double* X, double load_factor, double scale, int enforce_positive,
                     const double* g_out, double* g_theta, void* stream);
+/* y[i] = the tanh the hidden layers use (branch-free, absolute error <= 4.5e-16); exposed for its
+ * accuracy test.  x, y dev [n]. */
+int pf_debug_tanh(int64_t n, const double* x, double* y, void* stream);
 /* Jacobian rows d value_p / d theta for every point p: jac dev [n][n_params]
  * (what fem/nn_solver.py:91-110 obtains with one reverse pass per row). */
 int pf_mlp_param_jacobian(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta,

@@ -146,7 +146,7 @@ __device__ __forceinline__ void forward_hidden(const GdArgs& a, double* sm, int 
         const int in = l == 0 ? n.d.in_dim : n.d.w;
         const double* th = sm + a.o_theta + n.theta_off;
         const double z = th[n.d.b_off[l] + o] + dot4(th + n.d.w_off[l] + o * in, 1, act_ptr(a, n, sm, l) + e * in, 1, in);
-        sm[n.act_off + a.nelem * n.d.in_dim + l * a.nelem * n.d.w + qq] = tanh(z);
+        sm[n.act_off + a.nelem * n.d.in_dim + l * a.nelem * n.d.w + qq] = pf_tanh(z);
     }
 }
 

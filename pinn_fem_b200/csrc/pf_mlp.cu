@@ -87,10 +87,10 @@ __device__ __forceinline__ void hidden_layer(const double* __restrict__ Wt, cons
             acc2 = fma(w23.x, a, acc2);
             acc3 = fma(w23.y, a, acc3);
         }
-        a_out[(o0)*PS + t] = tanh(acc0);
-        a_out[(o0 + 1) * PS + t] = tanh(acc1);
-        a_out[(o0 + 2) * PS + t] = tanh(acc2);
-        a_out[(o0 + 3) * PS + t] = tanh(acc3);
+        a_out[(o0)*PS + t] = pf_tanh(acc0);
+        a_out[(o0 + 1) * PS + t] = pf_tanh(acc1);
+        a_out[(o0 + 2) * PS + t] = pf_tanh(acc2);
+        a_out[(o0 + 3) * PS + t] = pf_tanh(acc3);
     }
 }
 
@@ -489,6 +489,22 @@ extern "C" int pf_mlp_param_jacobian(pf_plan* plan, int input_dim, int hidden_la
     } while (0)
     PF_MLP_DISPATCH(pts, PF_JAC);
 #undef PF_JAC
+    PF_CUDA_CHECK(cudaGetLastError());
+    return PF_OK;
+}
+
+namespace {
+__global__ void tanh_probe_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = pf_tanh(x[i]);
+}
+}  // namespace
+
+// y[i] = pf_tanh(x[i]) (dev pointers): the hidden-layer activation of every MLP kernel, exposed for its accuracy test.
+extern "C" int pf_debug_tanh(int64_t n, const double* x, double* y, void* stream) {
+    PF_REQUIRE(n >= 0 && (n == 0 || (x && y)), "pf_debug_tanh: bad argument");
+    if (n == 0) return PF_OK;
+    tanh_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pf_stream_of(stream)>>>(n, x, y);
     PF_CUDA_CHECK(cudaGetLastError());
     return PF_OK;
 }

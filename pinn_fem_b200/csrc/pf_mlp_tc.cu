@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads) mlp_tc_kernel(PfMlpDesc d, const dou
                     for (int h = 0; h < 2; ++h) {
                         const int o = n0 + 2 * t4 + h;
                         // row w carries the ones the bias gradient needs; rows beyond hold tanh(0) = 0
-                        An[o * PS + tw0 + mt * 8 + g] = o == w ? 1.0 : tanh(c[mt][h]);
+                        An[o * PS + tw0 + mt * 8 + g] = o == w ? 1.0 : pf_tanh(c[mt][h]);
                     }
             }
             __syncwarp();
