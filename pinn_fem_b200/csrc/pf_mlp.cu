@@ -72,26 +72,34 @@ __device__ void stage_weights(const PfMlpDesc& d, const SmemPlan& s, const doubl
 }
 
 // One hidden layer for the calling thread's point: out[o][t] = tanh(b[o] + sum_i Wt[i][o] in[i][t]).
+template <int PS, int NO>
+__device__ __forceinline__ void hidden_block(const double* __restrict__ Wt, const double* __restrict__ b, int in, int wp,
+                                             const double* __restrict__ a_in, double* __restrict__ a_out, int t, int o0) {
+    double acc[NO];
+#pragma unroll
+    for (int j = 0; j < NO; ++j) acc[j] = b[o0 + j];
+    for (int i = 0; i < in; ++i) {
+        const double a = a_in[i * PS + t];
+#pragma unroll
+        for (int j = 0; j < NO; j += 2) {
+            const double2 w = *reinterpret_cast<const double2*>(Wt + i * wp + o0 + j);
+            acc[j] = fma(w.x, a, acc[j]);
+            acc[j + 1] = fma(w.y, a, acc[j + 1]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NO; ++j) a_out[(o0 + j) * PS + t] = pf_tanh(acc[j]);
+}
+
+// One hidden layer for the calling thread's point: out[o][t] = tanh(b[o] + sum_i Wt[i][o] in[i][t]); eight
+// outputs at a time (eight independent accumulator / tanh chains: the kernel is fp64-latency bound), then four.
 template <int PS>
 __device__ __forceinline__ void hidden_layer(const double* __restrict__ Wt, const double* __restrict__ b, int in,
                                              int wp, const double* __restrict__ a_in, double* __restrict__ a_out,
                                              int t) {
-    for (int o0 = 0; o0 < wp; o0 += 4) {
-        double acc0 = b[o0], acc1 = b[o0 + 1], acc2 = b[o0 + 2], acc3 = b[o0 + 3];
-        for (int i = 0; i < in; ++i) {
-            const double a = a_in[i * PS + t];
-            const double2 w01 = *reinterpret_cast<const double2*>(Wt + i * wp + o0);
-            const double2 w23 = *reinterpret_cast<const double2*>(Wt + i * wp + o0 + 2);
-            acc0 = fma(w01.x, a, acc0);
-            acc1 = fma(w01.y, a, acc1);
-            acc2 = fma(w23.x, a, acc2);
-            acc3 = fma(w23.y, a, acc3);
-        }
-        a_out[(o0)*PS + t] = pf_tanh(acc0);
-        a_out[(o0 + 1) * PS + t] = pf_tanh(acc1);
-        a_out[(o0 + 2) * PS + t] = pf_tanh(acc2);
-        a_out[(o0 + 3) * PS + t] = pf_tanh(acc3);
-    }
+    int o0 = 0;
+    for (; o0 + 8 <= wp; o0 += 8) hidden_block<PS, 8>(Wt, b, in, wp, a_in, a_out, t, o0);
+    for (; o0 < wp; o0 += 4) hidden_block<PS, 4>(Wt, b, in, wp, a_in, a_out, t, o0);
 }
 
 template <int PS>
