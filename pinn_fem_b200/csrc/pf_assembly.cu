@@ -304,6 +304,100 @@ __global__ void __launch_bounds__(kMaxBlockThreads) node_gather_kernel(GatherArg
     }
 }
 
+// ---------------------------------------------------------------------------
+// Single problem (B = 1), linear element: the reference's own use case on a large mesh (one NR / CG /
+// GD state).  The batched kernels read 48 bytes of plan data per incidence (indices + precomputed
+// geometry), which at B = 1 is three times the algorithmic traffic; here a thread owns a node, reads
+// the compact {elem, nbr} table (8 bytes per incidence) and recomputes {cos, sin, 1/l0} from the node
+// coordinates with the same correctly-rounded operations the plan used on the host, so the result
+// is bit-identical to the batched kernels.  Orientation does not matter: negating (cos, sin) leaves
+// every product of pf_linear_incidence unchanged.
+// ---------------------------------------------------------------------------
+struct B1Args {
+    const int32_t* __restrict__ inc_ptr;
+    const int2* __restrict__ inc2;
+    const double* __restrict__ nodes;
+    const uint8_t* __restrict__ dof_free;
+    const double* __restrict__ x;  // u (force) or v (mat-vec)
+    const double* __restrict__ E;
+    const double* __restrict__ A;
+    const double* __restrict__ f_ext;
+    double* __restrict__ f_out;
+    double* __restrict__ r_out;
+    double* __restrict__ half_sq_part;  // [gridDim.x]
+    unsigned long long* __restrict__ max_strain_bits;
+    int64_t nnode;
+    double load_factor;
+};
+
+template <int DIM, int MODE>
+__global__ void __launch_bounds__(256) node_gather_b1_kernel(B1Args a) {
+    __shared__ double s_red[8];
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double sq = 0.0, eps_abs = 0.0;
+    if (n < a.nnode) {
+        const double xs = a.x[n * DIM], ys = DIM == 2 ? a.x[n * DIM + 1] : 0.0;
+        const double px = a.nodes[n * DIM], py = DIM == 2 ? a.nodes[n * DIM + 1] : 0.0;
+        double fx = 0.0, fy = 0.0;
+        const int k1 = a.inc_ptr[n + 1];
+#pragma unroll 3
+        for (int k = a.inc_ptr[n]; k < k1; ++k) {
+            const int2 ic = __ldg(a.inc2 + k);
+            double4 geo;
+            double xo, yo = 0.0;
+            if (DIM == 2) {
+                const double2 pn = __ldg(reinterpret_cast<const double2*>(a.nodes) + ic.y);
+                const double2 un = __ldg(reinterpret_cast<const double2*>(a.x) + ic.y);
+                const double dx = __dsub_rn(pn.x, px), dy = __dsub_rn(pn.y, py);
+                const double l0 = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                geo = make_double4(__ddiv_rn(dx, l0), __ddiv_rn(dy, l0), __ddiv_rn(1.0, l0), l0);
+                xo = un.x;
+                yo = un.y;
+            } else {
+                const double l0 = fabs(__dsub_rn(__ldg(a.nodes + ic.y), px));
+                geo = make_double4(1.0, 0.0, __ddiv_rn(1.0, l0), l0);
+                xo = __ldg(a.x + ic.y);
+            }
+            const double eps = pf_linear_incidence<DIM>(__ldg(a.E + ic.x), __ldg(a.A + ic.x), geo, xs, ys, xo, yo, fx, fy);
+            if (MODE == MODE_FORCE) eps_abs = fmax(eps_abs, eps);
+        }
+        const int64_t d0 = n * DIM;
+        if (a.f_out) {
+            a.f_out[d0] = fx;
+            if (DIM == 2) a.f_out[d0 + 1] = fy;
+        }
+        if (MODE == MODE_FORCE && (a.r_out || a.half_sq_part)) {
+            const double rx = a.dof_free[d0] ? __dsub_rn(fx, __dmul_rn(a.load_factor, a.f_ext[d0])) : 0.0;
+            const double ry = (DIM == 2 && a.dof_free[d0 + 1]) ? __dsub_rn(fy, __dmul_rn(a.load_factor, a.f_ext[d0 + 1])) : 0.0;
+            if (a.r_out) {
+                a.r_out[d0] = rx;
+                if (DIM == 2) a.r_out[d0 + 1] = ry;
+            }
+            sq = rx * rx;
+            sq += ry * ry;
+        }
+    }
+    if (MODE == MODE_FORCE && (a.half_sq_part || a.max_strain_bits)) {  // fixed-order block reduction
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            eps_abs = fmax(eps_abs, __shfl_xor_sync(0xffffffffu, eps_abs, o));
+        }
+        if (a.half_sq_part) {
+            if (lane == 0) s_red[warp] = sq;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+                a.half_sq_part[blockIdx.x] = t;
+            }
+        }
+        if (a.max_strain_bits && lane == 0)
+            atomicMax(a.max_strain_bits, (unsigned long long)__double_as_longlong(eps_abs));
+    }
+}
+
 // out[b] = scale * sum_rows part[row][b], rows added in ascending order (deterministic).
 __global__ void column_sum_kernel(const double* __restrict__ part, int64_t rows, int64_t ld, int64_t B,
                                   double scale, double* __restrict__ out) {
@@ -663,6 +757,29 @@ static int launch_gather(pf_plan* plan, int kind, int mode, int64_t B, const dou
         const size_t rows = std::max<size_t>(plan->patches.size(), (size_t)plan->nnode);
         int rc = pf_plan_reserve_work(plan, rows * B * sizeof(double));
         if (rc) return rc;
+    }
+    static const int no_b1 = getenv("PF_NO_B1") ? atoi(getenv("PF_NO_B1")) : 0;
+    const bool x_al16 = (reinterpret_cast<uintptr_t>(mode == MODE_FORCE ? u : v) & 15) == 0;  // double2 loads of x
+    if (B == 1 && (kind == PF_ELEM_LINEAR || plan->dim == 1) && plan->nnode > 0 && !no_b1 && x_al16) {
+        // all B = 1 arrays are plain vectors whatever mat_batched / fext_batched say
+        const unsigned blocks = (unsigned)((plan->nnode + 255) / 256);
+        B1Args a{plan->d_inc_ptr, plan->d_inc2, plan->d_nodes, plan->d_dof_free, mode == MODE_FORCE ? u : v, E, A, f_ext,
+                 f_out, r, nullptr, max_strain ? reinterpret_cast<unsigned long long*>(max_strain) : nullptr,
+                 plan->nnode, load_factor};
+        if (half_sq) a.half_sq_part = plan->d_work;  // reserved above: >= nnode doubles
+        if (plan->dim == 1) {
+            if (mode == MODE_FORCE) node_gather_b1_kernel<1, MODE_FORCE><<<blocks, 256, 0, st>>>(a);
+            else node_gather_b1_kernel<1, MODE_MATVEC><<<blocks, 256, 0, st>>>(a);
+        } else {
+            if (mode == MODE_FORCE) node_gather_b1_kernel<2, MODE_FORCE><<<blocks, 256, 0, st>>>(a);
+            else node_gather_b1_kernel<2, MODE_MATVEC><<<blocks, 256, 0, st>>>(a);
+        }
+        PF_CUDA_CHECK(cudaGetLastError());
+        if (half_sq) {
+            column_sum_wide_kernel<<<1, 256, 0, st>>>(plan->d_work, blocks, 1, 0.5, half_sq);
+            PF_CUDA_CHECK(cudaGetLastError());
+        }
+        return PF_OK;
     }
     int64_t done = 0;
     if (kind == PF_ELEM_LINEAR || plan->dim == 1) {

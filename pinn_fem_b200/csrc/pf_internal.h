@@ -91,6 +91,8 @@ struct pf_plan {
     PfIncidence* d_inc = nullptr;       // [ninc]
     double4* d_inc_geo = nullptr;       // [ninc] {cos, sin, 1/l0, l0}
     double4* d_inc_xy = nullptr;        // [ninc] {x_nbr, y_nbr, x_self, y_self}
+    int2* d_inc2 = nullptr;             // [ninc] {elem, nbr}: the compact table of the single-problem kernels
+    double* d_nodes = nullptr;          // [nnode][dim] coordinates
     int32_t* d_diag_slot = nullptr;     // [nnode]
     int2* d_conn = nullptr;             // [nelem]
     double4* d_elem_geo = nullptr;      // [nelem] {cos, sin, 1/l0, l0}

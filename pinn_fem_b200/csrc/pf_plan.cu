@@ -346,6 +346,12 @@ extern "C" int pf_plan_upload(pf_plan* p, int device) {
     if ((rc = upload(&p->d_inc, inc))) return rc;
     if ((rc = upload(&p->d_inc_geo, inc_geo))) return rc;
     if ((rc = upload(&p->d_inc_xy, inc_xy))) return rc;
+    {
+        std::vector<int2> inc2(p->ninc);
+        for (int64_t k = 0; k < p->ninc; ++k) inc2[k] = make_int2((int)p->inc_elem[k], (int)p->inc_nbr[k]);
+        if ((rc = upload(&p->d_inc2, inc2))) return rc;
+        if ((rc = upload(&p->d_nodes, p->nodes))) return rc;
+    }
     if ((rc = upload(&p->d_diag_slot, diag32))) return rc;
     if ((rc = upload(&p->d_conn, conn))) return rc;
     if ((rc = upload(&p->d_elem_geo, elem_geo))) return rc;
@@ -406,7 +412,7 @@ extern "C" void pf_plan_destroy(pf_plan* p) {
     if (!p) return;
     if (p->device >= 0) {
         cudaSetDevice(p->device);
-        void* ptrs[] = {p->d_inc_ptr, p->d_inc, p->d_inc_geo, p->d_inc_xy, p->d_diag_slot, p->d_conn,
+        void* ptrs[] = {p->d_inc2, p->d_nodes, p->d_inc_ptr, p->d_inc, p->d_inc_geo, p->d_inc_xy, p->d_diag_slot, p->d_conn,
                         p->d_elem_geo, p->d_elem_xy, p->d_centroid, p->d_dof_free, p->d_free_dofs,
                         p->d_free_index, p->d_bsr_rowptr, p->d_bsr_colind, p->d_work, p->d_patches,
                         p->d_patch_nodes, p->d_patch_elems, p->d_patch_inc_ptr, p->d_patch_inc, p->d_patch_inc_geo};

@@ -246,3 +246,41 @@ def test_residual_host_roundtrip(plans):
     r_host = p.residual_host(u, E, A, fx, 0.8, chunk=64)
     r_dev = p.residual(u.cuda(), E.cuda(), A.cuda(), fx.cuda(), 0.8, f_int=False, r=True)["r"]
     assert torch.equal(r_host, r_dev.cpu())
+
+
+@pytest.mark.parametrize("mesh", ["lattice", "random_dups", "bar1d"])
+def test_single_problem_kernel_matches_batched_bitwise(plans, mesh):
+    """B = 1 goes through its own kernel (compact index table, geometry recomputed from the coordinates with
+    correctly-rounded operations): f_int, r and K v must carry the same bits as column 0 of a batched call."""
+    rng = np.random.default_rng(17)
+    if mesh == "lattice":
+        nodes, el, fixed = O.lattice_truss(9, 7)
+        nodes = nodes + rng.uniform(-0.2, 0.2, nodes.shape)
+        dim = 2
+    elif mesh == "random_dups":
+        nodes, el, fixed = _random_graph(5)
+        dim = 2
+    else:
+        nodes = np.sort(rng.uniform(0, 10, size=60))
+        el = np.concatenate([np.stack([np.arange(59), np.arange(1, 60)], axis=1), [[0, 7], [30, 10], [7, 0]]])
+        fixed, dim = [0, 59], 1
+    p = plans("b1_" + mesh, nodes, el, fixed, dim)
+    B = 3
+    u = rng.uniform(-1e-3, 1e-3, (p.ndof, B))
+    E = rng.uniform(0.5, 1.5, (len(el), B))
+    A = rng.uniform(0.5, 1.5, (len(el), B))
+    fx = rng.normal(size=p.ndof)
+    v = rng.normal(size=(p.ndof, B))
+    ob = p.residual(dev(u), dev(E), dev(A), dev(fx), 0.7, r=True, half_sq=True, max_strain=True)
+    kb = p.tangent_matvec(dev(v), dev(E), dev(A))
+    for b in range(B):
+        o1 = p.residual(dev(u[:, b].copy()), dev(E[:, b].copy()), dev(A[:, b].copy()), dev(fx), 0.7, r=True, half_sq=True,
+                        max_strain=True)
+        assert torch.equal(o1["f_int"], ob["f_int"][:, b]) and torch.equal(o1["r"], ob["r"][:, b])
+        assert float(o1["max_strain"][0]) == float(ob["max_strain"][b])
+        assert abs(float(o1["half_sq"][0]) / float(ob["half_sq"][b]) - 1.0) < 1e-13
+        k1 = p.tangent_matvec(dev(v[:, b].copy()), dev(E[:, b].copy()), dev(A[:, b].copy()))
+        assert torch.equal(k1, kb[:, b])
+    f_ref, eps_ref = O.assemble_residual(nodes, el, E[:, 0], A[:, 0], u[:, 0], dim)
+    o1 = p.residual(dev(u[:, 0].copy()), dev(E[:, 0].copy()), dev(A[:, 0].copy()), max_strain=True)
+    assert rel(o1["f_int"], f_ref) < TOL and rel(o1["max_strain"], np.atleast_1d(eps_ref)) < 1e-9
