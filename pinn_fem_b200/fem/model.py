@@ -1,40 +1,54 @@
-"""Data model (reference: fem/model.py): Material, FEMModel, legacy SolverConfig / SolverResult."""
+"""Data model of the drop-in layer: ``Material``, ``FEMModel`` and the legacy Newton ``SolverConfig`` /
+``SolverResult``.  Field names, defaults and the ValueError texts are the reference's contract
+(fem/model.py:12-107); the mesh itself ends up in an ``AssemblyPlan`` on the device (fem/_device.py)."""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+import dataclasses
 from typing import Dict, List
 
 import numpy as np
 
 from .properties import Property, to_property
 
+_PROPERTY_SLOTS = ("young", "area", "density")  # Material order = parameter order of the device loops
 
-@dataclass
+
+@dataclasses.dataclass
 class Material:
-    """young / area / density, each a scalar or a Property (fem/model.py:12-43)."""
+    """Three properties, each a plain number or a ``Property`` (scalar / network); plain numbers are
+    wrapped on construction so that callers can always use ``material.young.value(...)``."""
 
     young: Property | float
     area: Property | float
     density: Property | float = 0.0
 
     def __post_init__(self):
-        for name in ("young", "area", "density"):
-            setattr(self, name, to_property(getattr(self, name)))
+        for slot in _PROPERTY_SLOTS:
+            setattr(self, slot, to_property(getattr(self, slot)))
 
-    def _props(self):
-        return (self.young, self.area, self.density)
+    def properties(self):
+        return tuple(getattr(self, slot) for slot in _PROPERTY_SLOTS)
 
     def has_trainable_params(self) -> bool:
-        return any(p.is_trainable() for p in self._props())
+        return any(prop.is_trainable() for prop in self.properties())
 
     def get_all_torch_params(self) -> list:
-        out = []
-        for p in self._props():
-            out.extend(p.get_torch_params())
-        return out
+        return [p for prop in self.properties() for p in prop.get_torch_params()]
 
 
-@dataclass
+def _mesh_errors(model):
+    """(violated, message) pairs in the order the reference checks them."""
+    dim, nodes, el = model.dimension, model.nodes, model.elements
+    yield dim not in (1, 2), "dimension must be 1 or 2"
+    yield dim == 1 and nodes.ndim != 1, "For 1D, nodes must be 1D array of positions"
+    yield dim == 2 and (nodes.ndim != 2 or nodes.shape[1] != 2), "For 2D, nodes must have shape (nnode, 2)"
+    yield el.ndim != 2 or el.shape[1] != 2, "elements must have shape (nelm, 2)"
+    ndof = int(nodes.shape[0]) * dim
+    yield model.loads.size != ndof, f"loads size must be {ndof}, got {model.loads.size}"
+    yield bool(np.any((model.fixed_dofs < 0) | (model.fixed_dofs >= ndof))), "fixed_dofs contain out-of-range indices"
+
+
+@dataclasses.dataclass
 class FEMModel:
     nodes: np.ndarray
     elements: np.ndarray
@@ -44,49 +58,28 @@ class FEMModel:
     dimension: int = 2
 
     def __post_init__(self) -> None:
-        self.nodes = np.asarray(self.nodes, dtype=float)
-        self.elements = np.asarray(self.elements, dtype=int)
-        self.loads = np.asarray(self.loads, dtype=float).reshape(-1)
-        self.fixed_dofs = np.asarray(self.fixed_dofs, dtype=int).reshape(-1)
-        if self.dimension not in (1, 2):
-            raise ValueError("dimension must be 1 or 2")
-        if self.dimension == 1 and self.nodes.ndim != 1:
-            raise ValueError("For 1D, nodes must be 1D array of positions")
-        if self.dimension == 2 and (self.nodes.ndim != 2 or self.nodes.shape[1] != 2):
-            raise ValueError("For 2D, nodes must have shape (nnode, 2)")
-        if self.elements.ndim != 2 or self.elements.shape[1] != 2:
-            raise ValueError("elements must have shape (nelm, 2)")
-        if self.loads.size != self.ndof:
-            raise ValueError(f"loads size must be {self.ndof}, got {self.loads.size}")
-        if np.any(self.fixed_dofs < 0) or np.any(self.fixed_dofs >= self.ndof):
-            raise ValueError("fixed_dofs contain out-of-range indices")
+        for name, kind, flat in (("nodes", float, False), ("elements", int, False), ("loads", float, True),
+                                 ("fixed_dofs", int, True)):
+            arr = np.asarray(getattr(self, name), dtype=kind)
+            setattr(self, name, arr.reshape(-1) if flat else arr)
+        for violated, message in _mesh_errors(self):
+            if violated:
+                raise ValueError(message)
 
-    @property
-    def nnode(self) -> int:
-        return int(self.nodes.shape[0])
-
-    @property
-    def nelm(self) -> int:
-        return int(self.elements.shape[0])
-
-    @property
-    def ndof(self) -> int:
-        return self.nnode * self.dimension
+    nnode = property(lambda self: int(self.nodes.shape[0]))
+    nelm = property(lambda self: int(self.elements.shape[0]))
+    ndof = property(lambda self: self.nnode * self.dimension)
 
 
-@dataclass(frozen=True)
-class SolverConfig:
-    """Legacy NR configuration (fem/model.py:94-99)."""
+# legacy configuration / result of fem.core.solve_incremental_newton (fem/model.py:94-107)
+SolverConfig = dataclasses.make_dataclass(
+    "SolverConfig",
+    [("n_increments", int, 10), ("max_iterations", int, 80), ("tolerance", float, 1e-6), ("min_denominator", float, 1e-12)],
+    frozen=True)
+SolverConfig.__module__ = __name__
 
-    n_increments: int = 10
-    max_iterations: int = 80
-    tolerance: float = 1e-6
-    min_denominator: float = 1e-12
-
-
-@dataclass
-class SolverResult:
-    displacements: np.ndarray
-    reactions: np.ndarray
-    converged: bool
-    history: List[Dict[str, float]] = field(default_factory=list)
+SolverResult = dataclasses.make_dataclass(
+    "SolverResult",
+    [("displacements", np.ndarray), ("reactions", np.ndarray), ("converged", bool),
+     ("history", List[Dict[str, float]], dataclasses.field(default_factory=list))])
+SolverResult.__module__ = __name__
