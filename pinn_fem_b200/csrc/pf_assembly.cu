@@ -620,7 +620,7 @@ static int check_common(pf_plan* plan, int kind, int64_t B, const double* E, con
     PF_REQUIRE(kind == PF_ELEM_LINEAR || kind == PF_ELEM_GREEN_LAGRANGE, "unknown element kind %d", kind);
     PF_REQUIRE(!(kind == PF_ELEM_GREEN_LAGRANGE && plan->dim != 2), "Green-Lagrange element is 2-D only");
     PF_REQUIRE(B >= 1, "B must be >= 1");
-    PF_REQUIRE(E != nullptr && A != nullptr, "E/A is NULL");
+    PF_REQUIRE(plan->nelem == 0 || (E != nullptr && A != nullptr), "E/A is NULL");
     return PF_OK;
 }
 

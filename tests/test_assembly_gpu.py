@@ -284,3 +284,28 @@ def test_single_problem_kernel_matches_batched_bitwise(plans, mesh):
     f_ref, eps_ref = O.assemble_residual(nodes, el, E[:, 0], A[:, 0], u[:, 0], dim)
     o1 = p.residual(dev(u[:, 0].copy()), dev(E[:, 0].copy()), dev(A[:, 0].copy()), max_strain=True)
     assert rel(o1["f_int"], f_ref) < TOL and rel(o1["max_strain"], np.atleast_1d(eps_ref)) < 1e-9
+
+
+@pytest.mark.parametrize("B", [1, 5, 160])
+def test_isolated_nodes_and_empty_meshes(B):
+    """Nodes without elements get zero force and a zero diagonal block; a mesh without elements is all zeros
+    (single-problem, generic and patch-staged kernels)."""
+    from pinn_fem_b200 import AssemblyPlan
+
+    nodes = np.array([[0.0, 0], [1, 0], [5, 5], [2, 1], [9, 9]])
+    el = np.array([[0, 1], [1, 3], [3, 0]])
+    p = AssemblyPlan(nodes, el, [0, 1], device="cuda")
+    rng = np.random.default_rng(2)
+    shp = (lambda n: (n,)) if B == 1 else (lambda n: (n, B))
+    u, E, A = rng.normal(size=shp(10)), rng.uniform(0.5, 1.5, shp(3)), rng.uniform(0.5, 1.5, shp(3))
+    f = p.internal_force(dev(u), dev(E), dev(A)).cpu().numpy()
+    f_ref, _ = O.assemble_residual(nodes, el, E, A, u)
+    assert rel(f, f_ref) < TOL and np.all(f[[4, 5, 8, 9]] == 0.0)
+    vals = p.tangent_bsr(dev(E), dev(A)).cpu().numpy()
+    diag = p._array(10)  # PF_ARR_DIAG_SLOT
+    assert np.all(vals[diag[[2, 4]]] == 0.0)
+    empty = AssemblyPlan(nodes, np.zeros((0, 2), dtype=int), [], device="cuda")
+    z = torch.zeros(shp(0), dtype=torch.float64, device="cuda")
+    out = empty.residual(dev(u), z, z, dev(np.ones(10)), 2.0, r=True, half_sq=True)
+    assert float(out["f_int"].abs().max()) == 0.0
+    assert np.allclose(out["r"].cpu().numpy(), -2.0) and np.allclose(out["half_sq"].cpu().numpy(), 0.5 * 10 * 4.0)
