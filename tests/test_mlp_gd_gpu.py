@@ -244,7 +244,7 @@ def test_gd_on_a_larger_mesh_vs_oracle():
     assert rel(res.history[0, :25, 1], np.array([h["loss_total"] for h in hist])) < 1e-9
 
 
-@pytest.mark.parametrize("case", ["nets", "scalar_area", "converges"])
+@pytest.mark.parametrize("case", ["nets", "scalar_area", "converges", "all_scalar"])
 def test_gd_large_mesh_device_loop_vs_oracle(case):
     """Meshes that do not fit one CTA's shared memory run the same iteration as a device-resident
     sequence of kernels (pf_gd_large.cu): 40x40 lattice (4641 elements, MLP backward on DMMA), duplicate
@@ -267,6 +267,13 @@ def test_gd_large_mesh_device_loop_vs_oracle(case):
     elif case == "scalar_area":
         mat = O.MaterialNets((specs[0], th[0].copy(), 2.0), 1.5, 1.0)
         nets, scales, theta0 = [ops.NetSpec(3, 2, 20), None, None], [2.0, 1.5, 1.0], th[0]
+    elif case == "all_scalar":  # no network at all: only u is optimised (example 2 on a large mesh)
+        mat = O.MaterialNets(2.0, 1.5, 1.0)
+        nets, scales, theta0 = [None, None, None], [2.0, 1.5, 1.0], np.zeros(0)
+        # uniform materials on a regular lattice: many DOFs have gradients that cancel to round-off, and Adam's
+        # g / sqrt(v) normalisation turns a 1e-16 difference in summation order into +-lr steps within ~10
+        # iterations (the losses still agree to 1e-3 after 20); compare while the trajectories are comparable
+        n_it = 3
     else:  # loose tolerance: stops on the loss test right after iteration 11 (checked only for it > 10)
         mat = O.MaterialNets((specs[0], th[0].copy(), 2.0), (specs[1], th[1].copy(), 1.5), 1.0)
         nets, scales, theta0 = [ops.NetSpec(3, 2, 20), ops.NetSpec(3, 2, 15), None], [2.0, 1.5, 1.0], np.concatenate(th)
@@ -274,7 +281,7 @@ def test_gd_large_mesh_device_loop_vs_oracle(case):
     u_ref, reac_ref, ok, hist = O.solve_gd(mesh, mat, n_it, tol, lr_u=1e-4, lr_theta=1e-3, alpha_d=10.0,
                                            meas_dofs=md, meas_vals=mv, lam=0.9)
     plan = AssemblyPlan(nodes, el, fixed, device="cuda")
-    theta = dev(theta0)[None].clone()
+    theta = dev(theta0)[None].clone() if theta0.size else None
     res = ops.gd_solve(plan, nets, scales, theta, torch.zeros((1, plan.ndof), dtype=torch.float64, device="cuda"),
                        dev(loads), md, mv, max_iterations=n_it, tolerance=tol, learning_rate_u=1e-4,
                        learning_rate_theta=1e-3, alpha_data=10.0, load_factor=0.9)
@@ -283,13 +290,18 @@ def test_gd_large_mesh_device_loop_vs_oracle(case):
     if case == "converges":
         assert n == 12 and ok
     assert rel(res.u[0], u_ref) < 1e-9 and rel(res.reactions[0], reac_ref) < 1e-8
-    th_ref = np.concatenate([mat.young[1], mat.area[1]]) if case != "scalar_area" else mat.young[1]
-    assert rel(res.theta[0], th_ref) < 1e-9
+    if case == "all_scalar":
+        assert res.theta.numel() == 0
+    else:
+        th_ref = np.concatenate([mat.young[1], mat.area[1]]) if case != "scalar_area" else mat.young[1]
+        assert rel(res.theta[0], th_ref) < 1e-9
     for col, key in ((1, "loss_total"), (2, "loss_physics"), (3, "loss_data"), (4, "u_norm"), (5, "residual_norm"),
                      (6, "theta_norm")):
+        if key == "theta_norm" and case == "all_scalar":
+            continue
         assert rel(res.history[0, :n, col], np.array([h[key] for h in hist])) < 1e-9, key
     # bitwise reproducible
-    theta2 = dev(theta0)[None].clone()
+    theta2 = dev(theta0)[None].clone() if theta0.size else None
     res2 = ops.gd_solve(plan, nets, scales, theta2, torch.zeros((1, plan.ndof), dtype=torch.float64, device="cuda"),
                         dev(loads), md, mv, max_iterations=n_it, tolerance=tol, learning_rate_u=1e-4,
                         learning_rate_theta=1e-3, alpha_data=10.0, load_factor=0.9)
