@@ -419,3 +419,18 @@ def test_examples_9_and_10_run_where_the_reference_crashes(tmp_path, example_inp
     tol = 10 * float(d.get("solver_config", {}).get("tolerance", 1e-6))  # the solve stops at its own tolerance
     assert np.max(np.abs(f[free] - loads[free])) < tol * max(1.0, np.abs(loads).max())
     assert np.allclose(np.asarray(out["reactions"])[0], -loads.sum(), atol=tol)
+
+
+@pytest.mark.parametrize("name", ["example3-P", "example6-P", "example7-P"])
+def test_remaining_pinn_examples_against_reference_runs(tmp_path, example_inputs, runs, name):
+    """Whole generic.py runs of the other PINN examples (E = NN / hybrid with 1 and 3 networks), seed 0 on both
+    sides: same convergence flag, displacements within the GD tolerance of the reference's fp32 run, same schema."""
+    out = _run_generic(tmp_path, example_inputs[name], name=f"{name}.json")
+    ref = runs[name]["output"]
+    assert out["converged"] == ref["converged"] is True
+    assert np.allclose(out["displacements"], ref["displacements"], rtol=0, atol=5e-3)
+    assert np.allclose(out["displacements"], [0, 0, 1, 0, 2, 0, 3, 0], rtol=0, atol=5e-3)
+    assert sorted(out["nn_parameters"]) == sorted(ref["nn_parameters"])
+    assert set(out["history"][0]) == set(ref["history"][0])
+    for k, v in ref["nn_parameters"].items():
+        assert np.asarray(out["nn_parameters"][k]).shape == np.asarray(v).shape
