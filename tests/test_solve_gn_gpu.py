@@ -136,3 +136,27 @@ def test_jtj_dmma_random(m, n):
     assert rel(jtj, ref + d * np.eye(n)) < 1e-12
     assert rel(jtr, J.T @ R) < 1e-12
     assert torch.equal(jtj, jtj.T)
+
+
+@pytest.mark.parametrize("n", [1, 5, 32, 33, 100, 257, 1001, 2100])
+def test_cholesky_spd_solve(n):
+    """Blocked Cholesky (panel solve + DMMA trailing update + one-CTA triangular solves) against numpy, incl. ragged
+    last panels, and the not-positive-definite report."""
+    from pinn_fem_b200 import ops
+
+    rng = np.random.default_rng(n)
+    M = rng.normal(size=(n, n + 3))
+    A = M @ M.T + 1e-3 * np.eye(n)
+    b = rng.normal(size=n)
+    x_ref = np.linalg.solve(A, b)
+    Au = A.copy()
+    Au[np.triu_indices(n, 1)] = np.nan  # the upper triangle must not be read
+    x = ops.solve_spd(dev(Au), dev(b)).cpu().numpy()
+    assert np.linalg.norm(A @ x - b) <= 1e-10 * np.linalg.norm(A, 2) * np.linalg.norm(x_ref) * max(n, 1) ** 0.5 + 1e-12
+    assert np.linalg.norm(x - x_ref) <= 1e-8 * np.linalg.cond(A) ** 0.5 * np.linalg.norm(x_ref) + 1e-12
+    assert torch.equal(ops.solve_spd(dev(Au), dev(b)), ops.solve_spd(dev(Au), dev(b)))  # deterministic
+    if n >= 5:
+        bad = A.copy()
+        bad[n // 2, n // 2] = -1.0
+        with pytest.raises(RuntimeError, match="not positive definite"):
+            ops.solve_spd(dev(bad), dev(b))
