@@ -277,15 +277,7 @@ struct DevBuf {
     }
     int open(cudaStream_t s) {
         st = s;
-        static std::once_flag once;
-        std::call_once(once, [] {  // keep freed blocks cached in the pool instead of returning them at every sync
-            int dev = 0;
-            cudaMemPool_t pool;
-            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                uint64_t keep = UINT64_MAX;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-        });
+        pf_keep_pool_cached();
         return PF_OK;
     }
     template <typename T>

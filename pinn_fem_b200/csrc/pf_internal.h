@@ -128,6 +128,9 @@ struct pf_plan {
 };
 
 int pf_plan_reserve_work(pf_plan* plan, size_t bytes);
+// Raise the release threshold of the current device's default stream-ordered pool (once per device): freed
+// scratch stays cached instead of going back to the driver at every synchronisation.
+void pf_keep_pool_cached();
 
 // pf_patch.cu: shared-memory staged gather for wide batches (linear element).
 // Returns PF_OK and sets *handled when it ran; otherwise the caller uses the generic kernel.

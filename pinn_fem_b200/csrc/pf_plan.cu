@@ -306,6 +306,7 @@ extern "C" int pf_plan_upload(pf_plan* p, int device) {
     }
     PF_REQUIRE(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
     PF_CUDA_CHECK(cudaSetDevice(device));
+    pf_keep_pool_cached();
     PF_CUDA_CHECK(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device));
 
     const int dim = p->dim;
@@ -396,6 +397,19 @@ int pf_plan_activate(const pf_plan* p) {
     }
     PF_CUDA_CHECK(cudaSetDevice(p->device));
     return PF_OK;
+}
+
+void pf_keep_pool_cached() {
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    done[dev] = true;
 }
 
 int pf_plan_reserve_work(pf_plan* p, size_t bytes) {

@@ -264,6 +264,7 @@ extern "C" int pf_solve_dense(int64_t nbatch, int64_t n, double* A, double* b, i
         return PF_OK;
     }
     int32_t* piv = nullptr;
+    pf_keep_pool_cached();
     PF_CUDA_CHECK(cudaMallocAsync((void**)&piv, NB * sizeof(int32_t), st));
     PF_CUDA_CHECK(cudaMemsetAsync(info, 0, nbatch * sizeof(int32_t), st));
     for (int64_t m = 0; m < nbatch; ++m) {
