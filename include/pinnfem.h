@@ -227,8 +227,9 @@ int pf_gd_solve(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, double* t
  * A rank's local mesh lists its owned nodes first, then its halo nodes, and
  * holds every element incident to an owned node in ascending global element
  * id, so the owned rows of f_int carry the same bits as on a single GPU.
- * NCCL (resolved with dlopen at first use) moves the halo rows between
- * neighbours and all-reduces dL/dtheta and the loss scalars.  The reference
+ * The halo rows move between neighbours, and dL/dtheta and the loss scalars are
+ * all-reduced, through peer memory over NVLink (default) or NCCL (resolved with
+ * dlopen at first use).  The reference
  * has no counterpart: its dense K cannot hold such meshes (fem/assembly.py:19).
  *
  *   pf_comm_unique_id   rank 0 creates the 128-byte NCCL id, the host
@@ -246,6 +247,23 @@ int pf_comm_unique_id(unsigned char* id128);
 int pf_comm_create(int world, int rank, const unsigned char* id128, int device, pf_comm** out);
 void pf_comm_destroy(pf_comm* comm);
 int pf_comm_allreduce_sum(pf_comm* comm, double* buf, int64_t n, void* stream);
+/* Peer-memory transport (NVLink / NVSwitch, CUDA IPC; csrc/pf_peer.cuh).  Optional, collective:
+ *   pf_comm_peer_export   allocate this rank's mailbox (2 x world slots of halo_slot_doubles and of
+ *                         ar_slot_doubles, double buffered) and return its 64-byte IPC handle; the host
+ *                         all-gathers the handles (torch.distributed)
+ *   pf_comm_peer_import   handles [world][64] in rank order: map every peer's mailbox.  From here on
+ *                         pf_halo_exchange is ONE kernel that stores the halo rows straight into the
+ *                         neighbours' mailboxes, pf_comm_allreduce_sum sums in rank order (identical bits on
+ *                         every rank) and pf_gd_solve_sharded fuses the all-reduce into its Adam kernel;
+ *                         messages larger than a slot keep using NCCL
+ *   pf_comm_peer_detach   unmap the peers' mailboxes (NCCL transport from here on); call it on every rank,
+ *                         then synchronise the ranks, before pf_comm_destroy frees the own mailbox
+ *   pf_comm_peer_check    synchronise `stream`; PF_ERR_CUDA when a wait for a neighbour timed out (20 s) */
+int pf_comm_peer_export(pf_comm* comm, int64_t halo_slot_doubles, int64_t ar_slot_doubles, unsigned char* handle64);
+int pf_comm_peer_import(pf_comm* comm, const unsigned char* handles);
+int pf_comm_peer_enabled(const pf_comm* comm);
+void pf_comm_peer_detach(pf_comm* comm);
+int pf_comm_peer_check(pf_comm* comm, void* stream);
 int pf_halo_create(pf_comm* comm, int dim, int n_peers, const int32_t* peers, const int64_t* send_ptr,
                    const int32_t* send_nodes, const int64_t* recv_ptr, const int32_t* recv_nodes, pf_halo** out);
 void pf_halo_destroy(pf_halo* halo);

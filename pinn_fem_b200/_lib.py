@@ -104,6 +104,11 @@ SIGNATURES = {
     "pf_comm_create": (_int, [_int, _int, _vp, _int, C.POINTER(_vp)]),
     "pf_comm_destroy": (None, [_vp]),
     "pf_comm_allreduce_sum": (_int, [_vp, _vp, _i64, _vp]),
+    "pf_comm_peer_export": (_int, [_vp, _i64, _i64, _vp]),
+    "pf_comm_peer_import": (_int, [_vp, _vp]),
+    "pf_comm_peer_enabled": (_int, [_vp]),
+    "pf_comm_peer_detach": (None, [_vp]),
+    "pf_comm_peer_check": (_int, [_vp, _vp]),
     "pf_halo_create": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "pf_halo_destroy": (None, [_vp]),
     "pf_halo_exchange": (_int, [_vp, _vp, _i64, _vp]),

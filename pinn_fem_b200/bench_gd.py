@@ -151,8 +151,11 @@ def gd_element_sharded_iterations_per_second(device, nodes, elements, fixed, wor
                        f"({mesh.local.n_owned} owned + {mesh.local.halo.size} halo nodes on rank {comm.rank}), "
                        f"{iters} iterations", "scaling": "strong", "dtype": "f64", "ms_per_iteration": ms / iters,
            "iters_per_s": iters / (ms * 1e-3), "loop_only_ms_per_iteration": float(t2.item()) / iters,
-           "collectives_per_iteration": "2 halo exchanges (ncclSend/Recv group) + "
-                                                                            "1 all-reduce of 840 doubles",
+           "transport": comm.transport,
+           "collectives_per_iteration": ("2 halo exchanges (one kernel each: stores into the neighbours' mailboxes over "
+                                         "NVLink + epoch flag) + 1 all-reduce of 840 doubles fused into the Adam kernel"
+                                         if comm.transport == "peer" else
+                                         "2 halo exchanges (ncclSend/Recv group) + 1 all-reduce of 840 doubles"),
            "timed_region_includes": "host->device staging of the local vectors and the final halo exchange"}
     mesh.close()
     comm.close()

@@ -21,6 +21,7 @@
 
 #include "pf_internal.h"
 #include "pf_mlp.cuh"
+#include "pf_peer.cuh"
 
 namespace {
 
@@ -103,14 +104,39 @@ struct TensorList {
 
 // One block: Adam on the active parameters, per-tensor norms, u-norm second stage, history row,
 // convergence test (solver.py:308-355), iteration bookkeeping.
+// Element-sharded runs on the peer-memory transport (ar_n > 0): the all-reduce of the reduction buffer
+// g = [dL/dtheta | losses] over the ranks happens HERE, through the peers' mailboxes, before the update --
+// the collective and its consumer are one kernel (`losses` aliases the tail of g).
 __global__ void __launch_bounds__(1024) adam_theta_finish_kernel(LargeCfg c, int n_active, int n_theta, TensorList tl,
-                                                                 const double* __restrict__ g, double* __restrict__ theta,
+                                                                 double* g, double* __restrict__ theta,
                                                                  double* __restrict__ m, double* __restrict__ v,
-                                                                 const double* __restrict__ losses,
+                                                                 const double* losses,
                                                                  const double* __restrict__ upart, int n_upart,
-                                                                 double* __restrict__ sc, double* __restrict__ history) {
+                                                                 double* __restrict__ sc, double* __restrict__ history,
+                                                                 PfPeerView pv, int ar_n,
+                                                                 const double* __restrict__ rpart, int n_rpart) {
     __shared__ double tn[3 * 2 * (PF_MLP_MAX_LAYERS + 1)];
     __shared__ double ured[1024];
+    if (ar_n > 0) {
+        // this rank's 0.5 sum r^2 and sum u_free^2 (second stage of sq_partial_kernel / adam_u_kernel, fixed tree)
+        // go into the reduction buffer, then the buffer is summed over the ranks
+        for (int which = 0; which < 2; ++which) {
+            const double* part = which ? upart : rpart;
+            const int np = which ? n_upart : n_rpart;
+            double s = 0.0;
+            for (int b = threadIdx.x; b < np; b += blockDim.x) s += part[b];
+            ured[threadIdx.x] = s;
+            __syncthreads();
+            for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+                if (threadIdx.x < o) ured[threadIdx.x] += ured[threadIdx.x + o];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) g[n_theta + (which ? L_UNORM_SQ : L_HALF_SQ)] = which ? ured[0] : 0.5 * ured[0];
+            __syncthreads();
+        }
+        pf_peer_allreduce_block(pv, g, ar_n);  // ends with a block barrier
+        n_upart = 0;                           // the u norm now comes from the reduced buffer
+    }
     const bool done = sc[S_DONE] != 0.0;
     {   // ||u_free||^2: the partial sums of adam_u_kernel, folded by a fixed tree
         double s = 0.0;
@@ -307,10 +333,12 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
     // CUDA-graph replay of the iteration is available (PF_GD_GRAPH=1) but off by default: measured on B200 the
     // loop is GPU-bound, not launch-bound (1.30 ms eager vs 1.35-2.1 ms replayed on the 10^6-element lattice,
     // 0.27 vs 0.28-0.30 ms on 1.2 x 10^5 elements).
-    static const int no_graph = !(getenv("PF_GD_GRAPH") && atoi(getenv("PF_GD_GRAPH")));
+    const int no_graph = !(getenv("PF_GD_GRAPH") && atoi(getenv("PF_GD_GRAPH")));  // read per solve
     const int64_t ndof = plan->ndof, nelem = plan->nelem;
     const int64_t nd_own = sh ? sh->n_owned_nodes * plan->dim : ndof;  // rows this rank updates
     pf_comm* comm = sh ? pf_halo_comm(sh->halo) : nullptr;
+    PfPeerView pv;  // peer-memory transport: the all-reduce is fused into adam_theta_finish_kernel
+    const bool peer = comm && pf_comm_world(comm) > 1 && pf_comm_peer_view(comm, &pv);
     PF_REQUIRE(!sh || (sh->halo && nprob == 1 && sh->n_owned_nodes >= 0 && sh->n_owned_nodes <= plan->nnode),
                "pf_gd_solve_sharded: bad shard description");
     PfMlpDesc desc[3];
@@ -335,6 +363,7 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
     }
     // density never enters the physics: its gradient is None in the reference and Adam skips it
     const int n_active = cfg->net_enabled[2] ? theta_off[2] : ntheta;
+    const bool fused_ar = peer && ntheta + L_COUNT <= pv.ar_slot;
     const int n_meas = cfg->n_measured;                                   // measurements this rank holds
     const int n_meas_all = sh ? sh->n_measured_global : n_meas;           // of the whole mesh (the mean's divisor)
     const bool has_meas = n_meas_all > 0 && cfg->alpha_data > 0.0 && (sh || (meas_dofs && meas_vals_all));
@@ -367,7 +396,8 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
         (rc = buf.alloc(&fint, ndof)))
         return rc;
     const int ublocks = (int)std::min<int64_t>((ndof + kRedThreads - 1) / kRedThreads, 1024);
-    if ((rc = buf.alloc(&upart, ublocks))) return rc;
+    double* rpart;
+    if ((rc = buf.alloc(&upart, ublocks)) || (rc = buf.alloc(&rpart, ublocks))) return rc;
     if (has_meas && ((rc = buf.alloc(&msum, ndof)) || (rc = buf.alloc(&mcnt, ndof)))) return rc;
     // size the plan workspace once (residual partial sums, MLP gradient partials) so it is never
     // reallocated while iterations are in flight
@@ -460,8 +490,8 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
                     return rc;
                 // halo rows of the local residual are incomplete sums: drop them, then fetch the owners' values
                 if (ndof > nd_own) PF_CUDA_CHECK(cudaMemsetAsync(r + nd_own, 0, (ndof - nd_own) * sizeof(double), st));
-                sq_partial_kernel<<<ublocks, kRedThreads, 0, st>>>(r, nd_own, upart);
-                sum_partials_kernel<<<1, kRedThreads, 0, st>>>(upart, ublocks, 0.5, losses + L_HALF_SQ);
+                sq_partial_kernel<<<ublocks, kRedThreads, 0, st>>>(r, nd_own, rpart);
+                if (!fused_ar) sum_partials_kernel<<<1, kRedThreads, 0, st>>>(rpart, ublocks, 0.5, losses + L_HALF_SQ);
                 if ((rc = pf_halo_exchange(sh->halo, r, 1, st))) return rc;
             }
             // reverse pass: dL/du = gscale K r, dL/dE, dL/dA, dL/dtheta (closed form of the autograd graph)
@@ -476,14 +506,21 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
                                               gt + theta_off[k], st)))
                         return rc;
             }
-            if (local_meas) data_loss_kernel<<<1, kRedThreads, 0, st>>>(meas_dofs, mv, n_meas, u, losses);
+            // sharded: a rank without measurements of its own still resets its slot (the all-reduce left the
+            // global sum of the previous iteration there)
+            if (local_meas || (sh && has_meas))
+                data_loss_kernel<<<1, kRedThreads, 0, st>>>(meas_dofs, mv, local_meas ? n_meas : 0, u, losses);
             adam_u_kernel<<<ublocks, kRedThreads, 0, st>>>(c, nd_own, gu, msum, mcnt, plan->d_dof_free, u, mu, vu, sc, upart);
-            if (sh) {  // one all-reduce per iteration: [dL/dtheta | 0.5 sum r^2 | sum data^2 | sum u_free^2]
+            // sharded: one all-reduce per iteration of [dL/dtheta | 0.5 sum r^2 | sum data^2 | sum u_free^2] -- inside
+            // adam_theta_finish_kernel on the peer-memory transport (which also folds the two partial-sum
+            // buffers), an NCCL call otherwise
+            if (sh && !fused_ar) {
                 sum_partials_kernel<<<1, kRedThreads, 0, st>>>(upart, ublocks, 1.0, losses + L_UNORM_SQ);
                 if ((rc = pf_comm_allreduce_sum(comm, gt, ntheta + L_COUNT, st))) return rc;
             }
             adam_theta_finish_kernel<<<1, 1024, 0, st>>>(c, n_active, ntheta, tl, gt, theta, mt, vt, losses, upart,
-                                                        sh ? 0 : ublocks, sc, history);
+                                                        sh && !fused_ar ? 0 : ublocks, sc, history, pv,
+                                                        fused_ar ? ntheta + L_COUNT : 0, rpart, ublocks);
             PF_CUDA_CHECK(cudaGetLastError());
             return PF_OK;
         };
@@ -512,6 +549,7 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
                 PF_CUDA_CHECK(cudaMemcpyAsync(h_sc, sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
                 PF_CUDA_CHECK(cudaStreamSynchronize(st));
                 finished = h_sc[S_DONE] != 0.0;
+                if (peer && (rc = pf_comm_peer_check(comm, st))) return rc;  // a neighbour never arrived
             }
         }
         if (cfg->max_iterations == 0) {

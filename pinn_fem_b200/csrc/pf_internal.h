@@ -154,5 +154,7 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
 // pf_comm.cu
 int pf_comm_world(const pf_comm* c);
 pf_comm* pf_halo_comm(pf_halo* h);
+struct PfPeerView;
+bool pf_comm_peer_view(const pf_comm* c, PfPeerView* out);  // false: NCCL transport
 
 static inline cudaStream_t pf_stream_of(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -12,12 +12,14 @@ An element on a partition interface is local to both neighbours; its *owner* is 
 first node (only the owner contributes to ``dL/dtheta``).  The partition, halo and exchange lists
 are pure integer work done identically on every rank from the replicated global mesh: no
 communication is needed to set up.  At run time the ranks swap halo rows of ``u`` and ``r`` and
-all-reduce one short buffer per iteration (``pf_halo_exchange`` / ``pf_comm_allreduce_sum``: NCCL
-over NVLink, called from inside ``pf_gd_solve_sharded``).
+all-reduce one short buffer per iteration (``pf_halo_exchange`` / ``pf_comm_allreduce_sum``, called from
+inside ``pf_gd_solve_sharded``): through peer memory over NVLink -- the sending kernel stores into the
+receiver's mailbox, the all-reduce runs inside the Adam kernel -- or, without peer access, NCCL.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -140,10 +142,20 @@ def partition_mesh(nodes, elements, fixed_dofs, world: int, part: Optional[np.nd
 
 
 class Communicator:
-    """NCCL communicator owned by libpinnfem (``pf_comm``).  The 128-byte id is created on rank 0 and
-    broadcast with ``torch.distributed`` (any backend); collective over all ranks."""
+    """Communicator owned by libpinnfem (``pf_comm``): NCCL plus, when the GPUs can map each other's memory,
+    the peer-memory transport of ``csrc/pf_peer.cuh`` (halo rows stored straight into the neighbours'
+    mailboxes over NVLink, all-reduce fused into the consuming kernel).  The 128-byte NCCL id is created on
+    rank 0 and broadcast, the 64-byte CUDA IPC handles of the mailboxes are all-gathered, both with
+    ``torch.distributed`` (any backend); collective over all ranks.
 
-    def __init__(self, device, group=None):
+    ``transport``: ``"auto"`` (peer memory if every rank can set it up, else NCCL), ``"peer"`` (raise if it
+    cannot be set up) or ``"nccl"``; the environment variable ``PF_COMM_TRANSPORT`` overrides ``"auto"``.
+    ``self.transport`` holds the one in use, identical on every rank."""
+
+    HALO_SLOT_DOUBLES = 1 << 16  # per (parity, source rank): 32768 halo nodes of a 2-D single-problem vector
+    AR_SLOT_DOUBLES = 1 << 12
+
+    def __init__(self, device, group=None, transport="auto"):
         import torch
         import torch.distributed as dist
 
@@ -165,6 +177,63 @@ class Communicator:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.pf_comm_create(self.world, self.rank, idbuf, self.device.index or 0,
                                                 C.byref(self._handle)))
+        self._group = group
+        if transport == "auto":
+            transport = os.environ.get("PF_COMM_TRANSPORT", "auto")
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError(f"transport must be 'auto', 'peer' or 'nccl', got {transport!r}")
+        self.transport = "nccl"
+        if self.world > 1 and transport != "nccl":
+            self._setup_peer_transport(group, required=transport == "peer")
+
+    def _setup_peer_transport(self, group, required):
+        """Export this rank's mailbox, all-gather the IPC handles, map the peers' mailboxes.  Every step is
+        agreed on by all ranks (a rank that fails makes everybody fall back to NCCL, or raise)."""
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        on_gpu = dist.get_backend(group) == "nccl"
+        where = self.device if on_gpu else "cpu"
+
+        def all_ok(ok):
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=where)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(t.item())
+
+        hbuf = (C.c_ubyte * 64)()
+        err = ""
+        with torch.cuda.device(self.device):
+            rc = self._lib.pf_comm_peer_export(self._handle, self.HALO_SLOT_DOUBLES, self.AR_SLOT_DOUBLES, hbuf)
+            if rc != 0:
+                err = _lib.last_error()
+            mine = torch.tensor(list(hbuf), dtype=torch.uint8, device=where)
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine, group=group)  # also orders every rank's mailbox reset before any use
+            ok = all_ok(rc == 0)
+            if ok:
+                handles = (C.c_ubyte * (64 * self.world))(*torch.cat(parts).cpu().tolist())
+                rc = self._lib.pf_comm_peer_import(self._handle, handles)
+                if rc != 0:
+                    err = _lib.last_error()
+                ok = all_ok(rc == 0)
+            if ok:
+                self.transport = "peer"
+            else:
+                self._lib.pf_comm_peer_detach(self._handle)
+                if required:
+                    raise RuntimeError(f"peer-memory transport unavailable on rank {self.rank}: {err or 'a peer failed'}")
+
+    def check(self):
+        """Synchronise and raise if a peer-memory wait timed out (a neighbour never arrived)."""
+        import torch
+
+        from . import _lib
+
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pf_comm_peer_check(self._handle, C.c_void_p(
+                torch.cuda.current_stream(self.device).cuda_stream)))
 
     def allreduce_sum_(self, x):
         import torch
@@ -178,14 +247,23 @@ class Communicator:
                                                        C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return x
 
-    def close(self):
+    def close(self, _collective=True):
+        """Collective when the peer transport is on: every rank unmaps its peers' mailboxes before any rank
+        frees its own (CUDA IPC requires the importers to close first)."""
         if getattr(self, "_handle", None) and self._handle.value:
+            if getattr(self, "transport", "nccl") == "peer":
+                import torch.distributed as dist
+
+                self._lib.pf_comm_peer_detach(self._handle)
+                self.transport = "nccl"
+                if _collective and dist.is_available() and dist.is_initialized():
+                    dist.barrier(group=self._group)
             self._lib.pf_comm_destroy(self._handle)
             self._handle = C.c_void_p()
 
     def __del__(self):
         try:
-            self.close()
+            self.close(_collective=False)  # garbage collection is not synchronised between ranks: no barrier here
         except Exception:
             pass
 

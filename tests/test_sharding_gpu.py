@@ -140,6 +140,8 @@ loads = np.zeros(ndof); loads[-2], loads[-1] = 0.05, -0.02
 nets = [ops.NetSpec(3, 2, 20), ops.NetSpec(3, 2, 15), None]
 theta0 = rng.normal(scale=0.3, size=nets[0].n_params + nets[1].n_params)
 md = np.array([2 * 799, 2 * 799 + 1, 411, 411, 1202, 3100]); mv = np.array([0.01, -0.02, 0.005, 0.004, -0.003, 0.002])
+if os.environ.get("PF_MEAS_RANK0"):   # every measurement on rank 0's rows: the other rank holds none
+    md = np.array([2 * 799, 2 * 799 + 1, 411, 411, 1202, 1500])
 kw = dict(max_iterations=int(os.environ.get("PF_ITERS", "20")), tolerance=float(os.environ.get("PF_TOL", "1e-14")),
           learning_rate_u=1e-4, learning_rate_theta=1e-3, alpha_data=10.0, load_factor=0.9)
 out = gd_solve_element_sharded(mesh, nets, [2.0, 1.5, 1.0], theta0, np.zeros(ndof), loads, md, mv, **kw)
@@ -158,7 +160,7 @@ thetas = [torch.empty_like(out["theta"]) for _ in range(world)]
 if world > 1: dist.all_gather(thetas, out["theta"])
 else: thetas = [out["theta"]]
 if rank == 0:
-    torch.save({"world": world, "force_bitwise": force_bitwise, "allreduce": t.cpu(), "u": u_all.cpu(), "reac": reac_all.cpu(),
+    torch.save({"world": world, "transport": comm.transport, "force_bitwise": force_bitwise, "allreduce": t.cpu(), "u": u_all.cpu(), "reac": reac_all.cpu(),
                 "theta": out["theta"].cpu(), "theta_same": all(torch.equal(thetas[0], x) for x in thetas),
                 "hist": out["history"].cpu(), "n": out["n_iters"], "conv": out["converged"],
                 "u_ref": ref.u[0].cpu(), "reac_ref": ref.reactions[0].cpu(), "theta_ref": ref.theta[0].cpu(),
@@ -209,14 +211,51 @@ def test_element_sharded_world1_is_the_large_mesh_loop(tmp_path):
     assert torch.equal(g["u"], g["u_ref"]) and torch.equal(g["theta"], g["theta_ref"])
 
 
+def _peer_capable():
+    return torch.cuda.device_count() >= 2 and torch.cuda.can_device_access_peer(0, 1)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_element_sharded_two_gpus_match_single_gpu(tmp_path):
-    """Two ranks, NCCL halo exchange + gradient all-reduce: owned rows of f_int bitwise equal to the single-GPU
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_element_sharded_two_gpus_match_single_gpu(tmp_path, transport):
+    """Two ranks, halo exchange + gradient all-reduce over peer memory (stores into the neighbour's mailbox,
+    all-reduce fused into the Adam kernel) and over NCCL: owned rows of f_int bitwise equal to the single-GPU
     result, GD end state and history equal to 1e-10 (the all-reduce changes the summation order of dL/dtheta)."""
-    g = _run_elem(tmp_path, 2)
+    if transport == "peer" and not _peer_capable():
+        pytest.skip("GPUs 0 and 1 cannot map each other's memory")
+    env = {"PF_COMM_TRANSPORT": transport}
+    g = _run_elem(tmp_path, 2, env)
     assert g["world"] == 2 and g["allreduce"].tolist() == [1.0, 3.0, 5.0, 7.0]
+    assert g["transport"] == transport
     _check_elem(g)
     # early stop: every rank sees the same flag, at the iteration the single-GPU loop stops
-    g2 = _run_elem(tmp_path, 2, {"PF_ITERS": "40", "PF_TOL": "1e3"})
+    g2 = _run_elem(tmp_path, 2, dict(env, PF_ITERS="40", PF_TOL="1e3"))
     assert g2["n"] == g2["n_ref"] == 12 and g2["conv"] and g2["conv_ref"]
     _check_elem(g2)
+    # all measurements on rank 0's rows: rank 1 contributes an empty data loss every iteration
+    g3 = _run_elem(tmp_path, 2, dict(env, PF_MEAS_RANK0="1"))
+    _check_elem(g3)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 3, reason="needs more than two GPUs")
+def test_element_sharded_all_gpus_match_single_gpu(tmp_path):
+    """Every GPU of the box (interior ranks have two neighbours, the all-reduce sums world slots)."""
+    world = torch.cuda.device_count()
+    g = _run_elem(tmp_path, world, {"PF_COMM_TRANSPORT": "auto"})
+    assert g["world"] == world and g["allreduce"].tolist() == [sum(range(world)) + world * k for k in range(4)]
+    if all(torch.cuda.can_device_access_peer(0, d) for d in range(1, world)):
+        assert g["transport"] == "peer"
+    _check_elem(g)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_peer_and_nccl_transports_agree(tmp_path):
+    """Same run on both transports: u and f_int rows are bitwise equal (the halo rows carry the same values);
+    theta agrees to rounding (different all-reduce order)."""
+    if not _peer_capable():
+        pytest.skip("GPUs 0 and 1 cannot map each other's memory")
+    a = _run_elem(tmp_path, 2, {"PF_COMM_TRANSPORT": "peer", "PF_ITERS": "1"})
+    b = _run_elem(tmp_path, 2, {"PF_COMM_TRANSPORT": "nccl", "PF_ITERS": "1"})
+    assert a["transport"] == "peer" and b["transport"] == "nccl"
+    assert torch.equal(a["u"], b["u"])  # one iteration: u does not depend on the reduced gradient yet
+    assert _rel(a["theta"], b["theta"]) < 1e-13
