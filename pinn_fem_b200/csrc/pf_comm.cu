@@ -178,6 +178,8 @@ struct pf_halo {
     int64_t cap_B = 0;  // buffers hold cap_B problems
 };
 
+bool pf_halo_uses_peer(const pf_halo* h, int64_t B);
+
 extern "C" int pf_comm_available(void) { return nccl().ok ? 1 : 0; }
 
 extern "C" int pf_comm_unique_id(unsigned char* id128) {
@@ -376,7 +378,7 @@ extern "C" int pf_halo_exchange(pf_halo* h, double* x, int64_t B, void* stream) 
     cudaStream_t st = pf_stream_of(stream);
     const int64_t ns = h->send_ptr.back(), nr = h->recv_ptr.back();
     const int64_t row = (int64_t)h->dim * B;  // doubles per node
-    if (h->comm->peer_on && h->max_msg_nodes * row <= h->comm->view.halo_slot) {
+    if (pf_halo_uses_peer(h, B)) {
         const HaloLists l{h->d_peers, h->d_send_ptr, h->d_recv_ptr, h->d_send_nodes, h->d_recv_nodes};
         halo_peer_kernel<<<(unsigned)h->peers.size(), 512, 0, st>>>(h->comm->view, l, h->dim, B, x);
         PF_CUDA_CHECK(cudaGetLastError());
@@ -411,6 +413,9 @@ extern "C" int pf_halo_exchange(pf_halo* h, double* x, int64_t B, void* stream) 
 
 // accessors used by pf_gd_large.cu
 int pf_comm_world(const pf_comm* c) { return c ? c->world : 1; }
+bool pf_halo_uses_peer(const pf_halo* h, int64_t B) {
+    return h && h->comm->peer_on && h->max_msg_nodes * h->dim * B <= h->comm->view.halo_slot;
+}
 bool pf_comm_peer_view(const pf_comm* c, PfPeerView* out) {
     if (!c || !c->peer_on) return false;
     *out = c->view;

@@ -330,10 +330,6 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
     int wrc = ws.open(caller_st);
     if (wrc) return wrc;
     cudaStream_t st = ws.st;
-    // CUDA-graph replay of the iteration is available (PF_GD_GRAPH=1) but off by default: measured on B200 the
-    // loop is GPU-bound, not launch-bound (1.30 ms eager vs 1.35-2.1 ms replayed on the 10^6-element lattice,
-    // 0.27 vs 0.28-0.30 ms on 1.2 x 10^5 elements).
-    const int no_graph = !(getenv("PF_GD_GRAPH") && atoi(getenv("PF_GD_GRAPH")));  // read per solve
     const int64_t ndof = plan->ndof, nelem = plan->nelem;
     const int64_t nd_own = sh ? sh->n_owned_nodes * plan->dim : ndof;  // rows this rank updates
     pf_comm* comm = sh ? pf_halo_comm(sh->halo) : nullptr;
@@ -364,6 +360,14 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
     // density never enters the physics: its gradient is None in the reference and Adam skips it
     const int n_active = cfg->net_enabled[2] ? theta_off[2] : ntheta;
     const bool fused_ar = peer && ntheta + L_COUNT <= pv.ar_slot;
+    // The iteration is captured once and replayed as a CUDA graph (every argument is iteration-independent; the
+    // peer-memory epochs live in device memory).  Measured on B200, eager -> replayed: 1.144 -> 1.111 ms per
+    // iteration on the 10^6-element lattice, 0.464 -> 0.435 on 3.5 x 10^5 elements, 0.245 -> 0.213 on 1.25 x 10^5,
+    // 0.285 -> 0.260 element-sharded over 8 GPUs.  Runs with NCCL calls inside the iteration stay eager unless
+    // PF_GD_GRAPH=1 asks for capture; PF_GD_GRAPH=0 turns replay off.
+    const char* graph_env = getenv("PF_GD_GRAPH");  // read per solve
+    const bool nccl_in_loop = sh && pf_comm_world(comm) > 1 && !(fused_ar && pf_halo_uses_peer(sh->halo, 1));
+    const int no_graph = graph_env ? !atoi(graph_env) : (nccl_in_loop ? 1 : 0);
     const int n_meas = cfg->n_measured;                                   // measurements this rank holds
     const int n_meas_all = sh ? sh->n_measured_global : n_meas;           // of the whole mesh (the mean's divisor)
     const bool has_meas = n_meas_all > 0 && cfg->alpha_data > 0.0 && (sh || (meas_dofs && meas_vals_all));
@@ -473,9 +477,8 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
         };
 
         // one iteration = a fixed launch sequence whose arguments do not depend on the iteration index (the
-        // history row and beta^t come from device scalars), so it can be captured once into a CUDA graph --
-        // NCCL calls included -- and replayed (PF_GD_GRAPH=1; iteration 0 always runs eagerly: lazy
-        // allocations, function attributes).
+        // history row and beta^t come from device scalars), so it is captured once into a CUDA graph and
+        // replayed (iteration 0 always runs eagerly: lazy allocations, function attributes).
         auto iteration = [&]() -> int {
             if ((rc = materials())) return rc;
             // r = f_int - lambda f_ext on free DOFs, 0.5 sum r^2 (solver.py:262-270)

@@ -154,6 +154,7 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
 // pf_comm.cu
 int pf_comm_world(const pf_comm* c);
 pf_comm* pf_halo_comm(pf_halo* h);
+bool pf_halo_uses_peer(const pf_halo* h, int64_t B);  // this exchange goes through the peers' mailboxes
 struct PfPeerView;
 bool pf_comm_peer_view(const pf_comm* c, PfPeerView* out);  // false: NCCL transport
 

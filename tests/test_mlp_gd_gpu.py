@@ -308,6 +308,40 @@ def test_gd_large_mesh_device_loop_vs_oracle(case):
     assert torch.equal(res.u, res2.u) and torch.equal(res.theta, res2.theta)
 
 
+def test_gd_large_mesh_graph_replay_equals_eager(monkeypatch):
+    """The large-mesh loop replays its iteration as a CUDA graph by default; PF_GD_GRAPH=0 launches every kernel
+    eagerly.  Same kernels, same order: the results carry the same bits (also when the loop stops early)."""
+    from pinn_fem_b200 import AssemblyPlan, ops
+
+    nodes, el, fixed = O.lattice_truss(40)
+    rng = np.random.default_rng(5)
+    loads = np.zeros(2 * len(nodes))
+    loads[-2], loads[-1] = 0.05, -0.02
+    nets = [ops.NetSpec(3, 2, 20), ops.NetSpec(3, 2, 15), None]
+    theta0 = rng.normal(scale=0.3, size=nets[0].n_params + nets[1].n_params)
+    md, mv = np.array([2 * 799, 2 * 799 + 1, 411, 1202]), np.array([0.01, -0.02, 0.005, -0.003])
+    plan = AssemblyPlan(nodes, el, fixed, device="cuda")
+    for n_it, tol in ((30, 1e-14), (40, 1e3)):
+        out = {}
+        for mode in ("0", "1", None):
+            if mode is None:
+                monkeypatch.delenv("PF_GD_GRAPH", raising=False)
+            else:
+                monkeypatch.setenv("PF_GD_GRAPH", mode)
+            out[mode] = ops.gd_solve(plan, nets, [2.0, 1.5, 1.0], dev(theta0)[None].clone(),
+                                     torch.zeros((1, plan.ndof), dtype=torch.float64, device="cuda"), dev(loads), md, mv,
+                                     max_iterations=n_it, tolerance=tol, learning_rate_u=1e-4, learning_rate_theta=1e-3,
+                                     alpha_data=10.0, load_factor=0.9)
+        for mode in ("1", None):
+            a, b = out["0"], out[mode]
+            assert int(a.n_iters[0]) == int(b.n_iters[0]) and bool(a.converged[0]) == bool(b.converged[0])
+            assert torch.equal(a.u, b.u) and torch.equal(a.theta, b.theta) and torch.equal(a.reactions, b.reactions)
+            n = int(a.n_iters[0])
+            assert torch.equal(a.history[0, :n], b.history[0, :n])
+        if tol > 1:
+            assert int(out["0"].n_iters[0]) == 12
+
+
 def test_hidden_layer_tanh_accuracy():
     """The branch-free tanh of the MLP kernels: absolute error <= 4.5e-16 over the whole range, exact limits,
     odd symmetry, NaN propagation."""
