@@ -120,7 +120,11 @@ __global__ void __launch_bounds__(PatchCfg<CH>::kThreads, PatchCfg<CH>::kMinCtas
     int32_t* s_elems = s_nodes + a.max_local;
     int32_t* s_ptr = s_elems + a.max_elems;
     int32_t* s_free = s_ptr + kPatchNodes + 1;                       // [kPatchNodes*2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_free + kPatchNodes * 2) + 7) & ~uintptr_t(7));
+    // aligned by OFFSET from the shared array, not through uintptr_t: an integer round trip makes the compiler forget
+    // the address space and every access below becomes a generic LD/ST (long-scoreboard stalls in the copy loop)
+    const size_t bars_off =
+        ((size_t)(reinterpret_cast<unsigned char*>(s_free + kPatchNodes * 2) - smem_raw) + 7) & ~size_t(7);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + bars_off);
     const char** s_rowsrc = reinterpret_cast<const char**>(bars + 2);       // [stage_rows] global address of each staged row
     int64_t* s_outoff = reinterpret_cast<int64_t*>(s_rowsrc + stage_rows);  // [kPatchNodes] first DOF of the node * ldb
 
