@@ -365,9 +365,15 @@ int pf_gd_solve_large(pf_plan* plan, const pf_gd_config* cfg, int64_t nprob, dou
     // iteration on the 10^6-element lattice, 0.464 -> 0.435 on 3.5 x 10^5 elements, 0.245 -> 0.213 on 1.25 x 10^5,
     // 0.285 -> 0.260 element-sharded over 8 GPUs.  Runs with NCCL calls inside the iteration stay eager unless
     // PF_GD_GRAPH=1 asks for capture; PF_GD_GRAPH=0 turns replay off.
+    // Under a kernel profiler (ncu / nsys attach through a CUDA injection library) the loop also stays eager, so the
+    // profiler sees ordinary launches: ncu 2025.2 fails with LaunchFailed on the replayed mlp_tc_kernel node
+    // (101 KB of opt-in dynamic shared memory) although the same graph runs correctly -- and bitwise equal to the
+    // eager loop -- without it.
     const char* graph_env = getenv("PF_GD_GRAPH");  // read per solve
     const bool nccl_in_loop = sh && pf_comm_world(comm) > 1 && !(fused_ar && pf_halo_uses_peer(sh->halo, 1));
-    const int no_graph = graph_env ? !atoi(graph_env) : (nccl_in_loop ? 1 : 0);
+    const bool profiler = getenv("CUDA_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_PORT_BASE") ||
+                          getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NSYS_PROFILING_SESSION_ID");
+    const int no_graph = graph_env ? !atoi(graph_env) : (nccl_in_loop || profiler ? 1 : 0);
     const int n_meas = cfg->n_measured;                                   // measurements this rank holds
     const int n_meas_all = sh ? sh->n_measured_global : n_meas;           // of the whole mesh (the mean's divisor)
     const bool has_meas = n_meas_all > 0 && cfg->alpha_data > 0.0 && (sh || (meas_dofs && meas_vals_all));
