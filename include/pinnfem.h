@@ -258,7 +258,7 @@ int pf_comm_allreduce_sum(pf_comm* comm, double* buf, int64_t n, void* stream);
  *                         messages larger than a slot keep using NCCL
  *   pf_comm_peer_detach   unmap the peers' mailboxes (NCCL transport from here on); call it on every rank,
  *                         then synchronise the ranks, before pf_comm_destroy frees the own mailbox
- *   pf_comm_peer_check    synchronise `stream`; PF_ERR_CUDA when a wait for a neighbour timed out (20 s) */
+ *   pf_comm_peer_check    synchronise `stream`; PF_ERR_CUDA when a wait for a neighbour timed out (60 s) */
 int pf_comm_peer_export(pf_comm* comm, int64_t halo_slot_doubles, int64_t ar_slot_doubles, unsigned char* handle64);
 int pf_comm_peer_import(pf_comm* comm, const unsigned char* handles);
 int pf_comm_peer_enabled(const pf_comm* comm);
@@ -268,6 +268,10 @@ int pf_halo_create(pf_comm* comm, int dim, int n_peers, const int32_t* peers, co
                    const int32_t* send_nodes, const int64_t* recv_ptr, const int32_t* recv_nodes, pf_halo** out);
 void pf_halo_destroy(pf_halo* halo);
 int pf_halo_exchange(pf_halo* halo, double* x, int64_t B, void* stream);
+/* The transport of an exchange is chosen from the largest message (nodes) any rank sends or receives, so that
+ * all ranks choose alike: the host reduces that number over the ranks (MAX) and hands it back here. */
+int64_t pf_halo_max_message_nodes(const pf_halo* halo);
+int pf_halo_set_max_message_nodes(pf_halo* halo, int64_t global_max_nodes);
 
 typedef struct pf_gd_shard {
     pf_halo* halo;              /* exchange lists of this rank */

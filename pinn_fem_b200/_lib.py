@@ -112,6 +112,8 @@ SIGNATURES = {
     "pf_halo_create": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "pf_halo_destroy": (None, [_vp]),
     "pf_halo_exchange": (_int, [_vp, _vp, _i64, _vp]),
+    "pf_halo_max_message_nodes": (_i64, [_vp]),
+    "pf_halo_set_max_message_nodes": (_int, [_vp, _i64]),
     "pf_gd_solve_sharded": (_int, [_vp, C.POINTER(GDConfig), C.POINTER(GDShard), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _vp, _vp]),
 }

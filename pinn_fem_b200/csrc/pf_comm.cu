@@ -172,7 +172,7 @@ struct pf_halo {
     int32_t* d_peers = nullptr;      // device copies of peers / send_ptr / recv_ptr for the peer-memory kernel
     int64_t* d_send_ptr = nullptr;
     int64_t* d_recv_ptr = nullptr;
-    int64_t max_msg_nodes = 0;       // largest send or receive list of one neighbour
+    int64_t max_msg_nodes = 0;       // largest send or receive list of one neighbour (of ANY rank once the host has reduced it)
     double* d_send = nullptr;
     double* d_recv = nullptr;
     int64_t cap_B = 0;  // buffers hold cap_B problems
@@ -408,6 +408,16 @@ extern "C" int pf_halo_exchange(pf_halo* h, double* x, int64_t B, void* stream) 
     PF_NCCL_CHECK(nccl().GroupEnd());
     if (nr) halo_unpack_kernel<<<(unsigned)((nr * row + 255) / 256), 256, 0, st>>>(h->d_recv_nodes, nr, h->dim, B, h->d_recv, x);
     PF_CUDA_CHECK(cudaGetLastError());
+    return PF_OK;
+}
+
+extern "C" int64_t pf_halo_max_message_nodes(const pf_halo* h) { return h ? h->max_msg_nodes : 0; }
+
+extern "C" int pf_halo_set_max_message_nodes(pf_halo* h, int64_t global_max_nodes) {
+    PF_REQUIRE(h, "pf_halo_set_max_message_nodes: NULL halo");
+    PF_REQUIRE(global_max_nodes >= h->max_msg_nodes, "global maximum %lld is below this rank's own %lld",
+               (long long)global_max_nodes, (long long)h->max_msg_nodes);
+    h->max_msg_nodes = global_max_nodes;
     return PF_OK;
 }
 

@@ -22,7 +22,7 @@
 
 constexpr int kPfMaxRanks = 16;
 constexpr int64_t kPfMailboxHeader = 1024;
-constexpr unsigned long long kPfPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long kPfPeerTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;
 
 struct PfPeerView {
     int world = 1, rank = 0;

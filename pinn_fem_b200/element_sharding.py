@@ -288,6 +288,14 @@ class ShardedMesh:
         with torch.cuda.device(comm.device):
             _lib.check(self._lib.pf_halo_create(comm._handle, lm.dim, int(lm.peers.size), p(keep[0]), p(keep[1]),
                                                 p(keep[2]), p(keep[3]), p(keep[4]), C.byref(self._halo)))
+        if comm.world > 1:  # every rank must pick the same transport for an exchange: agree on the largest message
+            import torch.distributed as dist
+
+            on_gpu = dist.get_backend(comm._group) == "nccl"
+            t = torch.tensor([int(self._lib.pf_halo_max_message_nodes(self._halo))], dtype=torch.int64,
+                             device=comm.device if on_gpu else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=comm._group)
+            _lib.check(self._lib.pf_halo_set_max_message_nodes(self._halo, int(t.item())))
         self.elem_owned = torch.as_tensor(lm.elem_owned).to(comm.device)
         self.n_owned_dofs = lm.n_owned * lm.dim
 
