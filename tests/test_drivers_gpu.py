@@ -117,6 +117,35 @@ def test_fem2d_like_incremental_newton(golden_dir):
     assert abs(np.max(np.linalg.norm(res.displacements, axis=1)) - 6.344508621253013e-4) < 1e-11
 
 
+def test_newton_step_cholesky_first_then_lu_decides_singular():
+    """From 121 free DOFs on the Newton step tries the blocked Cholesky (K_ff is SPD on a constrained truss) and
+    agrees with the pivoted LU; a zero pivot (free node without elements) falls through to the LU and raises the
+    reference's RuntimeError (fem/core.py:36-37)."""
+    from oracle import pinnfem_oracle as O
+    from pinn_fem_b200 import AssemblyPlan, ops
+    from pinn_fem_b200.fem import core
+
+    nodes, el, fixed = O.lattice_truss(12)
+    rng = np.random.default_rng(2)
+    plan = AssemblyPlan(nodes, el, fixed, device="cuda")
+    assert plan.nfree >= core.SPD_FROM
+    E = torch.as_tensor(rng.uniform(0.5, 1.5, len(el))).cuda()
+    A = torch.as_tensor(rng.uniform(0.5, 1.5, len(el))).cuda()
+    rhs = torch.as_tensor(rng.normal(size=plan.ndof)).cuda()
+    u = torch.zeros(plan.ndof, dtype=torch.float64, device="cuda")
+    du = core.newton_step(plan, E, A, u, rhs)
+    free = torch.as_tensor(plan.free_dofs.copy(), device="cuda")
+    k_ff = plan.tangent_dense(E, A, u, free_only=True)
+    ref = ops.solve_dense(k_ff, rhs[free].contiguous())
+    assert rel(du[free], ref.cpu().numpy()) < 1e-11 and float(du.abs().sum() - du[free].abs().sum()) == 0.0
+    # one more node that no element touches: zero row and column in K_ff
+    nodes2 = np.vstack([nodes, [[99.0, 99.0]]])
+    plan2 = AssemblyPlan(nodes2, el, fixed, device="cuda")
+    with pytest.raises(RuntimeError, match="Tangent stiffness became singular"):
+        core.newton_step(plan2, E, A, torch.zeros(plan2.ndof, dtype=torch.float64, device="cuda"),
+                         torch.ones(plan2.ndof, dtype=torch.float64, device="cuda"))
+
+
 def test_incremental_newton_through_matrix_free_cg(golden_dir, monkeypatch):
     """Large meshes solve the Newton step with the matrix-free batched CG instead of dense LU; forcing that
     path on fem2d_like must reproduce the reference's displacements to the same 1e-8."""
