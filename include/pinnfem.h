@@ -298,7 +298,9 @@ int pf_gd_solve_sharded(pf_plan* plan, const pf_gd_config* cfg, const pf_gd_shar
  *   (np.linalg.solve in fem/core.py:35, fem/solver.py:464; torch.linalg.solve
  *   in fem/nn_solver.py:277).  A dev [nbatch][n][n] row-major (destroyed),
  *   b dev [nbatch][n] (overwritten with x), info dev int32 [nbatch]
- *   (0 ok, k>0: zero pivot at step k -> singular).
+ *   (0 ok, k>0: zero pivot at step k -> singular).  n <= 120: one CTA per
+ *   system in shared memory; larger n: blocked, the panel factorised by a
+ *   thread-block cluster in distributed shared memory.
  * pf_cg_solve: Jacobi-preconditioned conjugate gradients on the free DOFs of
  *   K_t(u) x = rhs, matrix-free, batched (x, rhs dev [ndof][B]; fixed DOFs are
  *   held at 0).  iters_out/resid_out host outputs; synchronises the stream.

@@ -5,17 +5,26 @@
 //    (fem/nn_solver.py:277).
 //      - n <= 120: one CTA per system, the augmented matrix [A | b] lives in
 //        shared memory (batched Newton steps on small meshes);
-//      - larger n: blocked right-looking LU in global memory (L2 resident up to
-//        n ~ 3000): single-CTA panel factorisation with warp-shuffle pivot
-//        search, then row swaps + triangular solve and a tiled rank-32 update
-//        spread over all SMs.  Used by the Gauss-Newton/LM step.
+//      - larger n: blocked right-looking LU in global memory: the 32-column panel
+//        is factorised by a thread-block CLUSTER of 8 CTAs that keeps the whole
+//        panel in distributed shared memory (pivot candidates and the pivot row
+//        travel over DSMEM, two cluster barriers per column), then row swaps +
+//        triangular solve and a tiled rank-32 update spread over all SMs.  Panels
+//        too tall for the cluster's shared memory (> ~6000 rows) use the
+//        single-CTA panel kernel.
 //  * pf_cg_solve: Jacobi-preconditioned conjugate gradients on the free DOFs,
 //    matrix-free through the assembly mat-vec kernel, batched over problems,
 //    with fixed-order (deterministic) two-stage dot products.
+#include <cooperative_groups.h>
+
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <cstdlib>
 
 #include "pf_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -161,6 +170,112 @@ __global__ void __launch_bounds__(1024) lu_panel_kernel(int n, int k0, int nb, d
     }
 }
 
+// The same panel factorisation on a thread-block cluster.  The single-CTA kernel above walks the panel 32 times
+// through one SM (1.0-1.3 ms per panel at n = 4096, 87 % of the whole solve).  Here the rows k0..n-1 are dealt in
+// contiguous slabs to the kLuCluster CTAs of a cluster and stay in their shared memory for all nb column steps;
+// global memory is touched twice (load, store).  Per column: local arg-max, every CTA pushes its candidate into
+// every other CTA's shared memory, cluster barrier, every CTA picks the winner (lowest index on ties: idamax)
+// and fetches the pivot row from its owner over DSMEM, cluster barrier, the two owners write the swapped rows,
+// local rank-1 update.  Arithmetic and pivot choice are those of lu_panel_kernel: same bits.
+constexpr int kLuCluster = 8;
+constexpr int kLuLd = NB + 1;  // odd row stride: column walks are bank-conflict free
+
+__global__ void __cluster_dims__(kLuCluster, 1, 1) __launch_bounds__(1024)
+    lu_panel_cluster_kernel(int n, int k0, int nb, int rows_per, double* __restrict__ A, int32_t* __restrict__ piv,
+                            int32_t* __restrict__ info) {
+    extern __shared__ double s_slab[];  // [rows_per][kLuLd]
+    __shared__ double s_cval[kLuCluster];
+    __shared__ int s_cidx[kLuCluster];
+    __shared__ double s_wval[32];
+    __shared__ int s_widx[32];
+    __shared__ double s_prow[NB], s_crow[NB];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int g0 = k0 + rank * rows_per;  // first global row of this CTA's slab
+    const int myrows = max(0, min(rows_per, n - g0));
+    for (int q = tid; q < myrows * nb; q += nt) {
+        const int r = q / nb, c = q - r * nb;
+        s_slab[r * kLuLd + c] = A[(size_t)(g0 + r) * n + k0 + c];
+    }
+    cluster.sync();  // every CTA of the cluster is running and has its slab before anyone touches remote shared memory
+    for (int j = 0; j < nb; ++j) {
+        const int col = k0 + j;
+        double best = -1.0;
+        int bi = INT_MAX;
+        for (int r = max(0, col - g0) + tid; r < myrows; r += nt) {
+            const double v = fabs(s_slab[r * kLuLd + j]);
+            if (v > best) {
+                best = v;
+                bi = g0 + r;
+            }
+        }
+        warp_argmax(best, bi);
+        if (lane == 0) {
+            s_wval[warp] = best;
+            s_widx[warp] = bi;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < nw ? s_wval[lane] : -1.0;
+            bi = lane < nw ? s_widx[lane] : INT_MAX;
+            warp_argmax(best, bi);
+            if (lane < kLuCluster) {  // this CTA's candidate goes into slot `rank` of CTA `lane`
+                cluster.map_shared_rank(s_cval, lane)[rank] = best;
+                cluster.map_shared_rank(s_cidx, lane)[rank] = bi;
+            }
+        }
+        cluster.sync();  // (1) all candidates have landed everywhere
+        double gb = -1.0;
+        int p = INT_MAX;
+#pragma unroll
+        for (int c = 0; c < kLuCluster; ++c) {
+            const double v = s_cval[c];
+            const int i = s_cidx[c];
+            if (v > gb || (v == gb && i < p)) {
+                gb = v;
+                p = i;
+            }
+        }
+        if (rank == 0 && tid == 0) {
+            piv[j] = p;
+            if (gb == 0.0 && *info == 0) *info = col + 1;
+        }
+        const int op = (p - k0) / rows_per, oc = (col - k0) / rows_per;  // owners of the pivot row and of row `col`
+        if (tid < nb) {  // everyone needs the pivot row; its owner also needs the row it trades places with
+            s_prow[tid] = cluster.map_shared_rank(s_slab, op)[(p - k0 - op * rows_per) * kLuLd + tid];
+            if (rank == op && p != col)
+                s_crow[tid] = cluster.map_shared_rank(s_slab, oc)[(col - k0 - oc * rows_per) * kLuLd + tid];
+        }
+        cluster.sync();  // (2) all remote reads are done before the owners overwrite the two rows
+        if (tid < nb && p != col) {
+            if (rank == oc) s_slab[(col - g0) * kLuLd + tid] = s_prow[tid];
+            if (rank == op) s_slab[(p - g0) * kLuLd + tid] = s_crow[tid];
+        }
+        __syncthreads();
+        const double pv = s_prow[j];
+        if (pv != 0.0) {
+            // one warp per row: lane c updates panel column j+1+c
+            for (int r = max(0, col + 1 - g0) + warp; r < myrows; r += nw) {
+                double l = 0.0;
+                if (lane == 0) {
+                    l = s_slab[r * kLuLd + j] / pv;
+                    s_slab[r * kLuLd + j] = l;
+                }
+                l = __shfl_sync(0xffffffffu, l, 0);
+                const int c = j + 1 + lane;
+                if (c < nb) s_slab[r * kLuLd + c] = fma(-l, s_prow[c], s_slab[r * kLuLd + c]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int q = tid; q < myrows * nb; q += nt) {
+        const int r = q / nb, c = q - r * nb;
+        A[(size_t)(g0 + r) * n + k0 + c] = s_slab[r * kLuLd + c];
+    }
+    cluster.sync();  // no CTA leaves while a neighbour could still be reading its shared memory
+}
+
 // Apply the panel's row swaps to the columns outside the panel (and to b), then solve
 // L11 * U12 = A12 for the columns right of the panel (and for b's top block).
 __global__ void lu_swap_trsm_kernel(int n, int k0, int nb, double* __restrict__ A, double* __restrict__ b,
@@ -230,20 +345,42 @@ __global__ void __launch_bounds__(256) lu_update_kernel(int n, int k0, int nb, d
     }
 }
 
-// x = U^{-1} y in place (column oriented, one CTA)
-__global__ void __launch_bounds__(1024) lu_backsolve_kernel(int n, const double* __restrict__ A,
-                                                            double* __restrict__ b) {
-    __shared__ double s_x;
-    for (int i = n - 1; i >= 0; --i) {
-        if (threadIdx.x == 0) {
-            const double d = A[(size_t)i * n + i];
-            s_x = d != 0.0 ? b[i] / d : b[i];
-            b[i] = s_x;
+// x = U^{-1} y in place.  One CTA of 32 warps walks the 32-row panels from the bottom: warp r forms the dot product of
+// row k0 + r with the part already solved (lanes stride along the row: coalesced; the column-oriented version read
+// every column with an n-double stride and took 7.5 ms at n = 4096), then warp 0 finishes the 32 x 32 upper triangle
+// out of shared memory.  Fixed summation order.  A zero diagonal entry divides by nothing (the caller reports
+// `info`), as before.
+__global__ void __launch_bounds__(1024) lu_backsolve_kernel(int n, const double* __restrict__ A, double* b) {
+    __shared__ double sT[NB][NB + 1];
+    __shared__ double sR[NB][33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int npanel = (n + NB - 1) / NB;
+    for (int p = npanel - 1; p >= 0; --p) {
+        const int k0 = p * NB, nb = min(NB, n - k0);
+        for (int q = tid; q < nb * nb; q += 1024) {
+            const int r = q / nb, c = q % nb;
+            sT[r][c] = c >= r ? A[(size_t)(k0 + r) * n + k0 + c] : 0.0;
         }
+        double acc = 0.0;
+        if (warp < nb)
+            for (int j = k0 + nb + lane; j < n; j += 32) acc = fma(A[(size_t)(k0 + warp) * n + j], b[j], acc);
+        sR[warp][lane] = acc;
         __syncthreads();
-        const double xi = s_x;
-        for (int r = threadIdx.x; r < i; r += blockDim.x) b[r] = fma(-A[(size_t)r * n + i], xi, b[r]);
-        __syncthreads();
+        if (warp == 0) {
+            double s = 0.0;
+            if (lane < nb)
+                for (int q = 0; q < 32; ++q) s += sR[lane][q];
+            double rhs = lane < nb ? b[k0 + lane] - s : 0.0;
+            for (int c = nb - 1; c >= 0; --c) {
+                const double d = sT[c][c];
+                const double num = __shfl_sync(0xffffffffu, rhs, c);
+                const double xc = d != 0.0 ? num / d : num;
+                if (lane == c) rhs = xc;
+                else if (lane < c) rhs = fma(-sT[lane][c], xc, rhs);
+            }
+            if (lane < nb) b[k0 + lane] = rhs;
+        }
+        __syncthreads();  // the solved block of b is visible to every warp before the next panel's dot products
     }
 }
 
@@ -263,6 +400,18 @@ extern "C" int pf_solve_dense(int64_t nbatch, int64_t n, double* A, double* b, i
         PF_CUDA_CHECK(cudaGetLastError());
         return PF_OK;
     }
+    // cluster panel: the first (tallest) panel decides the shared-memory opt-in; PF_LU_CLUSTER=0 keeps the single-CTA panel
+    const int env_cluster = getenv("PF_LU_CLUSTER") ? atoi(getenv("PF_LU_CLUSTER")) : 1;  // read per call
+    const size_t cluster_smem_max = 200 * 1024;
+    bool use_cluster = env_cluster != 0;
+    if (use_cluster) {
+        const size_t want = std::min(cluster_smem_max, (size_t)((n + kLuCluster - 1) / kLuCluster) * kLuLd * sizeof(double));
+        if (cudaFuncSetAttribute(lu_panel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            use_cluster = false;
+        }
+    }
     int32_t* piv = nullptr;
     pf_keep_pool_cached();
     PF_CUDA_CHECK(cudaMallocAsync((void**)&piv, NB * sizeof(int32_t), st));
@@ -272,7 +421,13 @@ extern "C" int pf_solve_dense(int64_t nbatch, int64_t n, double* A, double* b, i
         double* bm = b + (size_t)m * n;
         for (int k0 = 0; k0 < (int)n; k0 += NB) {
             const int nb = std::min<int>(NB, (int)n - k0);
-            lu_panel_kernel<<<1, 1024, 0, st>>>((int)n, k0, nb, Am, piv, info + m);
+            const int rows = (int)n - k0, rows_per = (rows + kLuCluster - 1) / kLuCluster;
+            const size_t slab = (size_t)rows_per * kLuLd * sizeof(double);
+            if (use_cluster && slab <= cluster_smem_max) {
+                lu_panel_cluster_kernel<<<kLuCluster, 1024, slab, st>>>((int)n, k0, nb, rows_per, Am, piv, info + m);
+            } else {
+                lu_panel_kernel<<<1, 1024, 0, st>>>((int)n, k0, nb, Am, piv, info + m);
+            }
             const int ncols = (int)n + 1 - nb;
             lu_swap_trsm_kernel<<<(ncols + 127) / 128, 128, 0, st>>>((int)n, k0, nb, Am, bm, piv);
             const int rem = (int)n - k0 - nb;

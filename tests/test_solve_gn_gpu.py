@@ -41,6 +41,34 @@ def test_dense_lu_solve(n, batch):
         assert rel(ops.solve_dense(dev(A[0]), dev(b[0])), x_ref[0]) < 1e-9
 
 
+@pytest.mark.parametrize("n", [121, 300, 1001, 1500])
+def test_lu_cluster_panel_equals_single_cta_panel(n, monkeypatch):
+    """The panel factorisation on a thread-block cluster (slabs in distributed shared memory) picks the same pivots
+    and does the same arithmetic as the single-CTA panel: identical bits, also with ties in the pivot search."""
+    from pinn_fem_b200 import ops
+
+    rng = np.random.default_rng(100 + n)
+    A = rng.normal(size=(n, n))
+    A[:, 0] = np.where(rng.random(n) < 0.5, 2.0, -2.0)   # every row ties in the first column: lowest index wins
+    A[5:40, 7] = 0.0
+    A[n // 2] = A[n // 3] * 1.0                          # duplicate row -> exactly singular
+    b = rng.normal(size=n)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PF_LU_CLUSTER", mode)
+        try:
+            outs[mode] = ops.solve_dense(dev(A), dev(b))
+        except RuntimeError:
+            outs[mode] = None
+    assert (outs["0"] is None) == (outs["1"] is None)
+    A[n // 2] = rng.normal(size=n)                       # regular again
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PF_LU_CLUSTER", mode)
+        outs[mode] = ops.solve_dense(dev(A), dev(b))
+    assert torch.equal(outs["0"], outs["1"])
+    assert rel(outs["1"], np.linalg.solve(A, b)) < 1e-8
+
+
 def test_dense_solve_singular_raises():
     from pinn_fem_b200 import ops
 
