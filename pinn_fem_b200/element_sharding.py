@@ -37,6 +37,36 @@ def contiguous_node_partition(nnode: int, world: int) -> np.ndarray:
     return part
 
 
+def coordinate_bisection_partition(nodes, world: int) -> np.ndarray:
+    """``part[n]`` = owner rank of node n by recursive coordinate bisection: the node set is cut across its longest
+    extent into two groups sized in proportion to the ranks they will hold, recursively, so every rank gets
+    ``nnode // world`` or one more nodes in a compact region whatever the node numbering (SURVEY.md 8e: "general
+    meshes: graph partition").  Ties are broken by node id, so the result is deterministic; contiguous id ranges
+    (``contiguous_node_partition``) are the special case of a mesh numbered along one axis."""
+    xy = np.asarray(nodes, dtype=np.float64)
+    if xy.ndim == 1:
+        xy = xy[:, None]
+    nnode = xy.shape[0]
+    if world < 1 or world > max(nnode, 1):
+        raise ValueError(f"cannot give {world} ranks at least one of {nnode} nodes each")
+    part = np.empty(nnode, dtype=np.int32)
+    counts = sharding.shard_counts(nnode, world)  # nodes per rank, in rank order
+    stack = [(np.arange(nnode, dtype=np.int64), 0, world)]
+    while stack:
+        ids, r0, nr = stack.pop()
+        if nr == 1:
+            part[ids] = r0
+            continue
+        half = nr // 2
+        n_left = int(sum(counts[r0:r0 + half]))
+        ext = xy[ids].max(axis=0) - xy[ids].min(axis=0)
+        axis = int(np.argmax(ext))
+        order = np.lexsort((ids, xy[ids, axis]))  # by coordinate, then by id
+        stack.append((ids[order[:n_left]], r0, half))
+        stack.append((ids[order[n_left:]], r0 + half, nr - half))
+    return part
+
+
 @dataclass
 class LocalMesh:
     """One rank's view of the partitioned mesh (host arrays; all ids int64 unless noted)."""

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import pinnfem_oracle as O
-from pinn_fem_b200.element_sharding import contiguous_node_partition, partition_mesh
+from pinn_fem_b200.element_sharding import contiguous_node_partition, coordinate_bisection_partition, partition_mesh
 from pinn_fem_b200.meshes import lattice_truss
 
 
@@ -21,7 +21,7 @@ def _random_mesh(seed):
 
 
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
-@pytest.mark.parametrize("mesh", ["lattice", "random", "random_part"])
+@pytest.mark.parametrize("mesh", ["lattice", "random", "random_part", "random_rcb"])
 def test_partition_is_consistent(world, mesh):
     part = None
     if mesh == "lattice":
@@ -30,6 +30,8 @@ def test_partition_is_consistent(world, mesh):
         nodes, el, fixed = _random_mesh(3)
         if mesh == "random_part":
             part = np.random.default_rng(1).integers(0, world, size=len(nodes)).astype(np.int32)
+        elif mesh == "random_rcb":
+            part = coordinate_bisection_partition(nodes, world)
     locs = partition_mesh(nodes, el, fixed, world, part)
     p = contiguous_node_partition(len(nodes), world) if part is None else part
     # every node owned once, every element owned once, local elements ascending in global id
@@ -74,6 +76,42 @@ def test_local_meshes_reproduce_global_internal_force_bitwise(world):
         nd = m.n_owned * m.dim
         got[m.local_dofs_global()[:nd]] = f_loc[:nd]
     assert np.array_equal(got, f_ref)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+def test_coordinate_bisection_partition_is_balanced_and_compact(world):
+    """Recursive coordinate bisection: rank sizes as balanced as contiguous ranges, deterministic, and -- on a
+    lattice whose nodes are numbered at random -- far fewer halo nodes than contiguous id ranges; the local
+    meshes still reproduce the global internal force bit for bit."""
+    nodes, el, fixed = lattice_truss(16, 12)
+    rng = np.random.default_rng(4)
+    perm = rng.permutation(len(nodes))            # new id of old node i
+    inv = np.argsort(perm)
+    nodes_s, el_s = nodes[inv], perm[np.asarray(el)]
+    fixed_s = (perm[np.asarray(fixed) // 2] * 2 + np.asarray(fixed) % 2)
+    part = coordinate_bisection_partition(nodes_s, world)
+    assert np.array_equal(part, coordinate_bisection_partition(nodes_s, world))
+    sizes = np.bincount(part, minlength=world)
+    assert sizes.max() - sizes.min() <= 1 and sizes.sum() == len(nodes)
+    locs = partition_mesh(nodes_s, el_s, fixed_s, world, part)
+    if world > 1:
+        halo_rcb = sum(m.halo.size for m in locs)
+        halo_ids = sum(m.halo.size for m in partition_mesh(nodes_s, el_s, fixed_s, world))
+        assert halo_rcb < 0.5 * halo_ids
+    u = rng.uniform(-1e-3, 1e-3, 2 * len(nodes))
+    E = rng.uniform(0.5, 1.5, len(el))
+    A = rng.uniform(0.5, 1.5, len(el))
+    f_ref, _ = O.assemble_residual(nodes_s, el_s, E, A, u)
+    got = np.full_like(f_ref, np.nan)
+    for m in locs:
+        f_loc, _ = O.assemble_residual(m.nodes, m.elements, E[m.elements_global], A[m.elements_global], m.to_local_vector(u))
+        nd = m.n_owned * m.dim
+        got[m.local_dofs_global()[:nd]] = f_loc[:nd]
+    assert np.array_equal(got, f_ref)
+    # 1-D coordinates and the error contract
+    assert np.array_equal(coordinate_bisection_partition(np.arange(10.0), 2), np.repeat([0, 1], 5))
+    with pytest.raises(ValueError):
+        coordinate_bisection_partition(nodes[:3], 4)
 
 
 def test_bad_partition_is_rejected():
