@@ -169,6 +169,22 @@ int pf_mlp_forward(pf_plan* plan, int input_dim, int hidden_layers, int width, c
 int pf_mlp_backward(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta, int64_t n,
                     const double* X, double load_factor, double scale, int enforce_positive,
                     const double* g_out, double* g_theta, void* stream);
+/* Batched networks with saved activations -- the kernels of the large-mesh / batched PINN loops (one launch per
+ * network for all problems, DMMA, register-resident layer chain).  Problem p uses theta + p * theta_stride and
+ * column p of out / g_out, both dev [n][ldb] (ldb >= B).  The forward leaves, per problem, a record of
+ * pf_mlp_acts_len(...) doubles (hidden activations and d value / d z) in acts[p]; the backward consumes it instead
+ * of recomputing the forward pass (tanh' = 1 - a^2).  acts may be NULL in the forward (nothing saved), out may be
+ * NULL when acts is given.  Shapes covered: input_dim <= 3, width <= 24, 1-3 hidden layers; pf_mlp_acts_len
+ * returns 0 for other shapes and the batched calls then fail with PF_ERR_ARG.
+ *   g_theta  dev [B][gt_stride] out (first n_params entries of every row; deterministic reduction order) */
+int64_t pf_mlp_acts_len(int input_dim, int hidden_layers, int width, int64_t n);
+int pf_mlp_forward_batched(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta,
+                           int64_t theta_stride, int64_t B, int64_t n, const double* X, double load_factor,
+                           double scale, int enforce_positive, double* out, int64_t ldb, double* acts, void* stream);
+int pf_mlp_backward_batched(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta,
+                            int64_t theta_stride, int64_t B, int64_t n, const double* X, double load_factor,
+                            const double* g_out, int64_t ldb, const double* acts, double* g_theta, int64_t gt_stride,
+                            void* stream);
 /* y[i] = the tanh the hidden layers use (branch-free, absolute error <= 4.5e-16); exposed for its
  * accuracy test.  x, y dev [n]. */
 int pf_debug_tanh(int64_t n, const double* x, double* y, void* stream);

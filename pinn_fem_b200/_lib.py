@@ -88,6 +88,11 @@ SIGNATURES = {
     "pf_mlp_num_params": (_i64, [_int, _int, _int]),
     "pf_mlp_forward": (_int, [_vp, _int, _int, _int, _vp, _i64, _vp, _dbl, _dbl, _int, _vp, _vp]),
     "pf_mlp_backward": (_int, [_vp, _int, _int, _int, _vp, _i64, _vp, _dbl, _dbl, _int, _vp, _vp, _vp]),
+    "pf_mlp_acts_len": (_i64, [_int, _int, _int, _i64]),
+    "pf_mlp_forward_batched": (_int, [_vp, _int, _int, _int, _vp, _i64, _i64, _i64, _vp, _dbl, _dbl, _int, _vp, _i64, _vp,
+                                      _vp]),
+    "pf_mlp_backward_batched": (_int, [_vp, _int, _int, _int, _vp, _i64, _i64, _i64, _vp, _dbl, _vp, _i64, _vp, _vp, _i64,
+                                       _vp]),
     "pf_mlp_param_jacobian": (_int, [_vp, _int, _int, _int, _vp, _i64, _vp, _dbl, _dbl, _int, _vp, _vp]),
     "pf_gd_solve": (_int, [_vp, C.POINTER(GDConfig), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pf_solve_dense": (_int, [_i64, _i64, _vp, _vp, _vp, _vp]),

@@ -52,10 +52,12 @@ __device__ void factor_diag(double (*sL)[NB + 1], int nb, int* bad) {
     __syncthreads();
 }
 
-// Panel step: diagonal block + the rows below it.  grid.x = 1 + ceil((n - k0 - nb) / PROWS); CTA 0 also writes
-// the factored diagonal block back and reports a non-positive pivot.
+// Panel step: diagonal block + the rows below it.  grid.x = 1 + ceil((n - k0 - nb) / PROWS).  Every CTA factors the
+// (unfactored) diagonal block it reads from A; CTA 0 stores the factor into the scratch `Ld` -- NOT into A: a CTA
+// that is scheduled late must still find the unfactored block there -- and reports a non-positive pivot.  The next
+// launch in stream order (chol_syrk_kernel, or chol_diag_store_kernel for the last panel) copies Ld into A.
 __global__ void __launch_bounds__(PROWS) chol_panel_kernel(int n, int k0, int nb, double* __restrict__ A,
-                                                           int32_t* __restrict__ info) {
+                                                           double* __restrict__ Ld, int32_t* __restrict__ info) {
     __shared__ double sL[NB][NB + 1];
     __shared__ double sP[PROWS][NB + 1];
     __shared__ int bad;
@@ -73,10 +75,7 @@ __global__ void __launch_bounds__(PROWS) chol_panel_kernel(int n, int k0, int nb
         return;
     }
     if (blockIdx.x == 0) {
-        for (int q = tid; q < nb * nb; q += PROWS) {
-            const int r = q / nb, c = q % nb;
-            if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = sL[r][c];
-        }
+        for (int q = tid; q < nb * nb; q += PROWS) Ld[q] = sL[q / nb][q % nb];
         return;
     }
     // rows i0 .. i0 + PROWS of the panel: X = A[i][k0:k0+nb] L^-T, staged through shared memory so that
@@ -113,9 +112,25 @@ __global__ void __launch_bounds__(PROWS) chol_panel_kernel(int n, int k0, int nb
 
 // Trailing update: C[i][j] -= sum_k P[i][k] P[j][k] for i >= j in [t0, n), P = A[:, k0:k0+NB] (full panels only;
 // the ragged last panel has no trailing matrix).  CTA tile 64 x 64, 4 warps of 32 x 32, lower tiles only.
-__global__ void __launch_bounds__(128) chol_syrk_kernel(int n, int k0, int t0, double* __restrict__ A) {
+__device__ __forceinline__ void store_diag(int n, int k0, int nb, const double* __restrict__ Ld, double* __restrict__ A) {
+    for (int q = threadIdx.x; q < nb * nb; q += blockDim.x) {
+        const int r = q / nb, c = q % nb;
+        if (c <= r) A[(size_t)(k0 + r) * n + k0 + c] = Ld[q];
+    }
+}
+
+__global__ void __launch_bounds__(128) chol_diag_store_kernel(int n, int k0, int nb, const double* __restrict__ Ld,
+                                                              double* __restrict__ A) {
+    store_diag(n, k0, nb, Ld, A);
+}
+
+__global__ void __launch_bounds__(128) chol_syrk_kernel(int n, int k0, int t0, const double* __restrict__ Ld,
+                                                        double* __restrict__ A) {
     const int bi = blockIdx.y, bj = blockIdx.x;
     if (bj > bi) return;
+    // the panel kernel has finished (stream order): its factored diagonal block goes into A now; no tile of this
+    // launch touches those entries
+    if (bi == 0 && bj == 0) store_diag(n, k0, NB, Ld, A);
     __shared__ double sI[TS][PLD];
     __shared__ double sJ[TS][PLD];
     const int i0 = t0 + bi * TS, j0 = t0 + bj * TS;
@@ -221,17 +236,24 @@ extern "C" int pf_solve_spd(int64_t n64, double* A, double* b, int32_t* info, vo
     const int n = (int)n64;
     cudaStream_t st = pf_stream_of(stream);
     PF_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+    pf_keep_pool_cached();
+    double* Ld = nullptr;  // factored diagonal block of the current panel (see chol_panel_kernel)
+    PF_CUDA_CHECK(cudaMallocAsync((void**)&Ld, NB * NB * sizeof(double), st));
     for (int k0 = 0; k0 < n; k0 += NB) {
         const int nb = std::min(NB, n - k0);
         const int below = n - k0 - nb;
-        chol_panel_kernel<<<1 + (below + PROWS - 1) / PROWS, PROWS, 0, st>>>(n, k0, nb, A, info);
-        if (below > 0) {
+        chol_panel_kernel<<<1 + (below + PROWS - 1) / PROWS, PROWS, 0, st>>>(n, k0, nb, A, Ld, info);
+        if (below > 0) {  // then nb == NB
             const int tiles = (below + TS - 1) / TS;
-            chol_syrk_kernel<<<dim3(tiles, tiles), 128, 0, st>>>(n, k0, k0 + nb, A);
+            chol_syrk_kernel<<<dim3(tiles, tiles), 128, 0, st>>>(n, k0, k0 + nb, Ld, A);
+        } else {
+            chol_diag_store_kernel<<<1, 128, 0, st>>>(n, k0, nb, Ld, A);
         }
     }
     chol_trisolve_kernel<false><<<1, 1024, 0, st>>>(n, A, b);
     chol_trisolve_kernel<true><<<1, 1024, 0, st>>>(n, A, b);
-    PF_CUDA_CHECK(cudaGetLastError());
+    const cudaError_t le = cudaGetLastError();
+    PF_CUDA_CHECK(cudaFreeAsync(Ld, st));
+    PF_CUDA_CHECK(le);
     return PF_OK;
 }

@@ -11,6 +11,7 @@
 
 #include "pf_internal.h"
 #include "pf_mlp.cuh"
+#include "pf_mlp_frag.h"
 
 namespace {
 
@@ -340,6 +341,10 @@ static bool tc_enabled() {
     static const int off = getenv("PF_MLP_NO_TC") ? atoi(getenv("PF_MLP_NO_TC")) : 0;
     return !off;
 }
+static bool frag_enabled() {
+    const char* e = getenv("PF_MLP_NO_FRAG");  // read per call: the tests flip it
+    return !(e && atoi(e));
+}
 
 static int pick_pts(const PfMlpDesc& d, bool backward, int* pts, size_t* smem) {
     for (int cand : {128, 64, 32}) {
@@ -381,6 +386,10 @@ extern "C" int pf_mlp_forward(pf_plan* plan, int input_dim, int hidden_layers, i
     PF_REQUIRE(out != nullptr, "out is NULL");
     if (n == 0) return PF_OK;
     cudaStream_t st = pf_stream_of(stream);
+    // large point sets: the register-resident DMMA kernel (pf_mlp_frag.cu); PF_MLP_NO_FRAG=1 keeps the older kernels
+    if (n >= kTcMinPoints && frag_enabled() && pf_mlp_frag_supported(d, false))
+        return pf_mlp_frag_forward(d, theta, 0, 1, n, X, cen, load_factor, scale, enforce_positive, out, 1, nullptr, 0,
+                                   sm_count_of(plan), st);
     // forward alone is bound by the 2 x w tanh evaluations per point, not by the contractions: the FMA
     // kernel (no padded columns) is faster there; PF_MLP_FWD_TC=1 selects the DMMA kernel anyway
     const char* fwd_env = getenv("PF_MLP_FWD_TC");  // read per call: the tests flip it
@@ -440,6 +449,19 @@ extern "C" int pf_mlp_backward(pf_plan* plan, int input_dim, int hidden_layers, 
         PF_CUDA_CHECK(cudaMemsetAsync(g_theta, 0, d.n_params * sizeof(double), st));
         return PF_OK;
     }
+    if (n >= kTcMinPoints && frag_enabled() && pf_mlp_frag_supported(d, true)) {
+        // forward into a scratch activation record (values not written), then the backward that consumes it
+        const int sms = sm_count_of(plan);
+        const int64_t acts_len = pf_mlp_frag_acts_len(d, n);
+        const size_t part_len = ((size_t)pf_mlp_frag_chunks(d, n, 1, sms) * d.n_params + 1) & ~size_t(1);
+        double* buf = nullptr;
+        if ((rc = scratch(plan, (part_len + (size_t)acts_len) * sizeof(double), &buf))) return rc;
+        if ((rc = pf_mlp_frag_forward(d, theta, 0, 1, n, X, cen, load_factor, scale, enforce_positive, nullptr, 1,
+                                      buf + part_len, 0, sms, st)))
+            return rc;
+        return pf_mlp_frag_backward(d, theta, 0, 1, n, X, cen, load_factor, g_out, 1, buf + part_len, 0, buf, g_theta, 0,
+                                    sms, st);
+    }
     if (n >= kTcMinPoints && tc_enabled()) {
         const int grid = pf_mlp_tc_grid(d, true, n, sm_count_of(plan));
         if (grid > 0) {
@@ -473,6 +495,49 @@ extern "C" int pf_mlp_backward(pf_plan* plan, int input_dim, int hidden_layers, 
         PF_CUDA_CHECK(cudaGetLastError());
     }
     return PF_OK;
+}
+
+extern "C" int64_t pf_mlp_acts_len(int input_dim, int hidden_layers, int width, int64_t n) {
+    PfMlpDesc d;
+    if (pf_mlp_make_desc(input_dim, hidden_layers, width, &d) != PF_OK || n < 0) return -1;
+    return pf_mlp_frag_supported(d, true) ? pf_mlp_frag_acts_len(d, n) : 0;
+}
+
+extern "C" int pf_mlp_forward_batched(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta,
+                                      int64_t theta_stride, int64_t B, int64_t n, const double* X, double load_factor,
+                                      double scale, int enforce_positive, double* out, int64_t ldb, double* acts,
+                                      void* stream) {
+    PfMlpDesc d;
+    const double* cen;
+    int rc = mlp_common(plan, input_dim, hidden_layers, width, theta, n, X, &d, &cen);
+    if (rc) return rc;
+    PF_REQUIRE(B >= 0 && ldb >= B && theta_stride >= 0, "pf_mlp_forward_batched: bad batch arguments");
+    PF_REQUIRE(out != nullptr || acts != nullptr, "out and acts are both NULL");
+    PF_REQUIRE(pf_mlp_frag_supported(d, acts != nullptr),
+               "network shape %d-%dx%d not covered by the batched kernels (input_dim <= 3, width <= 24, <= 3 hidden layers)",
+               input_dim, hidden_layers, width);
+    return pf_mlp_frag_forward(d, theta, theta_stride, B, n, X, cen, load_factor, scale, enforce_positive, out, ldb, acts,
+                               pf_mlp_frag_acts_len(d, n), sm_count_of(plan), pf_stream_of(stream));
+}
+
+extern "C" int pf_mlp_backward_batched(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta,
+                                       int64_t theta_stride, int64_t B, int64_t n, const double* X, double load_factor,
+                                       const double* g_out, int64_t ldb, const double* acts, double* g_theta,
+                                       int64_t gt_stride, void* stream) {
+    PfMlpDesc d;
+    const double* cen;
+    int rc = mlp_common(plan, input_dim, hidden_layers, width, theta, n, X, &d, &cen);
+    if (rc) return rc;
+    PF_REQUIRE(B >= 0 && ldb >= B && theta_stride >= 0 && gt_stride >= d.n_params, "pf_mlp_backward_batched: bad batch arguments");
+    PF_REQUIRE(g_out && g_theta && acts, "pf_mlp_backward_batched: NULL argument (acts comes from pf_mlp_forward_batched)");
+    PF_REQUIRE(pf_mlp_frag_supported(d, true),
+               "network shape %d-%dx%d not covered by the batched kernels (input_dim <= 3, width <= 24, <= 3 hidden layers)",
+               input_dim, hidden_layers, width);
+    const int sms = sm_count_of(plan);
+    double* part = nullptr;
+    if ((rc = scratch(plan, (size_t)B * pf_mlp_frag_chunks(d, n, B, sms) * d.n_params * sizeof(double), &part))) return rc;
+    return pf_mlp_frag_backward(d, theta, theta_stride, B, n, X, cen, load_factor, g_out, ldb, acts,
+                                pf_mlp_frag_acts_len(d, n), part, g_theta, gt_stride, sms, pf_stream_of(stream));
 }
 
 extern "C" int pf_mlp_param_jacobian(pf_plan* plan, int input_dim, int hidden_layers, int width,

@@ -1,0 +1,696 @@
+// Material networks, register-resident on the fp64 tensor pipe (DMMA, mma.sync.m8n8k4.f64): the kernels of the
+// large-mesh and batched PINN loops.
+//
+// SimpleNN (examples/json/generic.py:118-142) wrapped by NNProperty.value (fem/properties.py:150-156):
+// softplus(net(x)) * scale at ~10^6 element centroids per problem and iteration (fem/solver.py:252-355).
+//
+// What the probes on B200 said (profiles/r2_fp64_pipe_probe.md): DMMA and DFMA share ONE pipe (any mix sums to
+// ~33 TFLOP/s), a warp-wide fp64 op occupies a sub-partition for 2 cycles, a DMMA for 16, and the hidden-layer tanh
+// costs as much pipe time as 18-28 DFMAs.  So the cost of an iteration is the number of fp64 operations it issues,
+// and the kernels here are built to issue as few as possible and to keep the pipe fed without block barriers:
+//
+//  * forward (frag_forward_kernel): a warp owns 8 points (one DMMA m-tile) at a time and chains the layers in
+//    registers -- the C fragment of layer l (point g, two output columns per lane and n-tile) IS the A fragment of
+//    layer l+1 once the k index of that GEMM is permuted accordingly (the permutation is folded into the staged
+//    weights, which are read as one conflict-free LDS.64 per DMMA).  Padding columns (w = 20 -> 24) are arranged so
+//    that no lane evaluates a tanh for them and no k-step is spent on them.  The hidden activations and
+//    d value / d z are written to HBM in exactly this fragment order (coalesced 256/512-byte warp stores).
+//  * backward (frag_backward_kernel): reads the saved activations back (no forward recompute, no tanh at all:
+//    tanh' = 1 - a^2), back-propagates the deltas through register fragments the same way, and forms the weight
+//    gradients dW_l = D_l a_l^T (K = points) from a warp-private transposition of the two operand tiles through
+//    swizzled shared memory (conflict-free STS.128 in, LDS.64 out).  The gradient accumulators live in registers for
+//    the warp's whole share of the points; warps and CTAs are folded once at the end in a fixed order.
+//  * both kernels take a batch of problems (blockIdx.x = problem: per-problem theta, strided columns of
+//    out[point][ldb]); problems that share a point tile run next to each other so that L2 merges the 8-byte columns.
+//
+// Saving the activations costs (2 w + 1) * 8 bytes per point each way (328 B for 3-20-20-1) while the backward loses
+// 40 tanh + 480 MACs per point: on B200 the traffic hides behind the fp64 pipe.
+#include <cmath>
+#include <mutex>
+
+#include "pf_internal.h"
+#include "pf_mlp.cuh"
+#include "pf_mlp_frag.h"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kTRows = 32;                 // rows of a transposition tile (>= 8 * NTA)
+constexpr int kTDoubles = 8 * kTRows;      // 8 points x 32 rows
+
+enum { KIND_HALF = 0, KIND_PART = 1, KIND_FULL = 2 };
+
+__constant__ double c_exp2_tab[64];  // 2^(j/64)
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// tanh with a 64-entry 2^(j/64) table (shared memory) and a degree-5 polynomial: 18 fp64 operations instead of the
+// 28 of pf_tanh, same absolute error (2.9e-16 measured over [-22, 22]); tanh(0) = 0 exactly, NaN propagates.
+__device__ __forceinline__ double tanh_tab(double x, const double* __restrict__ tab) {
+    const double ax = fabs(x);
+    const double y = ax < 20.0 ? ax + ax : 40.0;  // tanh(20) rounds to 1
+    const double shifter = 6755399441055744.0;    // 1.5 * 2^52
+    const double t = fma(y, 1.4426950408889634 * 64.0, shifter);
+    const int n = __double2loint(t);
+    const double nf = t - shifter;
+    double r = fma(nf, -6.93147180369123816490e-01 / 64.0, y);
+    r = fma(nf, -1.90821492927058770002e-10 / 64.0, r);
+    double p = fma(r, 8.333333333333333e-03, 4.1666666666666664e-02);  // exp(r), |r| <= ln2 / 128
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    p *= tab[n & 63];
+    const double e = __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));  // p * 2^(n / 64)
+    const double d = e + 1.0;
+    double q;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(d));
+    q = fma(q, fma(-d, q, 1.0), q);
+    q = fma(q, fma(-d, q, 1.0), q);
+    const double res = fma(-2.0, q, 1.0);
+    return x != x ? x : copysign(res, x);
+}
+
+// Column slots of a w-wide activation in fragment order.  Lane (g = lane / 4, t4 = lane % 4) holds, for point g of
+// the m-tile, the slots (nt, h): nt < NT n-tiles, h < 2.  Logical column of a slot: 8 nt + 2 t4 + h, except in the
+// last tile of a HALF network (w = 8 (NT - 1) + b, 0 < b <= 4), where only h = 0 exists and stands for column
+// 8 nt + t4 -- so that no lane carries a padding-only slot.  k-step ks of a GEMM over such an activation is the
+// slot pair (nt = ks / 2, h = ks % 2): its four k values are the columns the four lanes of a quad hold there.
+template <int NT, int KIND>
+struct Frag {
+    static constexpr int KS = 2 * NT - (KIND == KIND_HALF ? 1 : 0);
+    static constexpr int NTA = NT + (KIND == KIND_FULL ? 1 : 0);  // n-tiles of [a; 1] (the ones row gives the bias gradient)
+    __host__ __device__ static constexpr bool has(int nt, int h) { return !(KIND == KIND_HALF && nt == NT - 1 && h == 1); }
+    __host__ __device__ static int col(int nt, int t4, int h) {
+        if (KIND == KIND_HALF && nt == NT - 1) return h ? (1 << 20) : 8 * nt + t4;
+        return 8 * nt + 2 * t4 + h;
+    }
+};
+
+// shared-memory plan (doubles)
+struct FragSmem {
+    int tab;                              // 64
+    int wf0;                              // [NT][32]
+    int wf[PF_MLP_MAX_LAYERS];            // l >= 1: [KS][NT][32]
+    int bias[PF_MLP_MAX_LAYERS];          // l >= 1: [NT][8]
+    int wo, bo;                           // [NT][8], 2
+    int wb[PF_MLP_MAX_LAYERS];            // l >= 1: [KS][NT][32] (backward)
+    int T;                                // [kWarps][3][kTDoubles]  (backward)
+    int red;                              // [n_params]              (backward)
+    int total;
+};
+
+__host__ __device__ inline FragSmem frag_smem(const PfMlpDesc& d, int NT, int KS, bool backward) {
+    FragSmem s;
+    int off = 0;
+    s.tab = off;
+    off += 64;
+    s.wf0 = off;
+    off += NT * 32;
+    for (int l = 0; l < PF_MLP_MAX_LAYERS; ++l) s.wf[l] = s.bias[l] = s.wb[l] = 0;
+    for (int l = 1; l < d.L; ++l) {
+        s.wf[l] = off;
+        off += KS * NT * 32;
+        s.bias[l] = off;
+        off += NT * 8;
+    }
+    s.wo = off;
+    off += NT * 8;
+    s.bo = off;
+    off += 2;
+    s.T = s.red = off;
+    if (backward) {
+        for (int l = 1; l < d.L; ++l) {
+            s.wb[l] = off;
+            off += KS * NT * 32;
+        }
+        s.T = off;
+        off += kWarps * 3 * kTDoubles;
+        s.red = off;
+        off += (d.n_params + 1) & ~1;
+    }
+    s.total = off;
+    return s;
+}
+
+struct FragArgs {
+    PfMlpDesc d;
+    FragSmem s;              // shared-memory plan (computed on the host)
+    const double* theta;
+    int64_t theta_stride;
+    int64_t n;               // points
+    int64_t units;           // ceil(n / 32)
+    int64_t units_per_chunk;
+    const double* X;         // [n][in_dim] or NULL
+    const double* centroid;  // [n][in_dim - 1]
+    double load_factor, scale;
+    int positive;
+    double* out;             // [n][ldb], column p
+    int64_t ldb;
+    double* acts;            // per problem: [L][4 units][KS][32] hidden activations, then [32 units] d value / d z
+    int64_t acts_stride;
+    const double* g_out;     // [n][ldb]
+    double* part;            // [B][nchunks][n_params]
+};
+
+template <int NT, int KIND>
+__device__ __forceinline__ void stage_weights(const PfMlpDesc& d, const FragSmem& s, const double* __restrict__ theta,
+                                              double* __restrict__ sm, bool backward) {
+    using F = Frag<NT, KIND>;
+    const int tid = threadIdx.x, w = d.w;
+    for (int q = tid; q < 64; q += kThreads) sm[s.tab + q] = c_exp2_tab[q];
+    // layer 0: B[k = t4][n = g] = W_0[out][t4], k = in_dim carries the bias (the input fragment holds a one there)
+    for (int q = tid; q < NT * 32; q += kThreads) {
+        const int nt = q >> 5, lane = q & 31, g = lane >> 2, t4 = lane & 3;
+        const int o = F::col(nt, g >> 1, g & 1);
+        double v = 0.0;
+        if (o < w) v = t4 < d.in_dim ? theta[d.w_off[0] + o * d.in_dim + t4] : (t4 == d.in_dim ? theta[d.b_off[0] + o] : 0.0);
+        sm[s.wf0 + q] = v;
+    }
+    for (int l = 1; l < d.L; ++l) {
+        const double* W = theta + d.w_off[l];
+        for (int q = tid; q < F::KS * NT * 32; q += kThreads) {
+            const int lane = q & 31, g = lane >> 2, t4 = lane & 3;
+            const int nt = (q >> 5) % NT, ks = (q >> 5) / NT;
+            const int cn = F::col(nt, g >> 1, g & 1);      // n index of the fragment
+            const int ck = F::col(ks >> 1, t4, ks & 1);    // k index of the fragment
+            // forward: z[out = cn] += a[in = ck] W[cn][ck];  backprop: e[in = cn] += D[out = ck] W[ck][cn]
+            sm[s.wf[l] + q] = (cn < w && ck < w) ? W[cn * w + ck] : 0.0;
+            if (backward) sm[s.wb[l] + q] = (cn < w && ck < w) ? W[ck * w + cn] : 0.0;
+        }
+        for (int q = tid; q < NT * 8; q += kThreads) {
+            const int c = F::col(q >> 3, (q & 7) >> 1, q & 1);
+            sm[s.bias[l] + q] = c < w ? theta[d.b_off[l] + c] : 0.0;
+        }
+    }
+    for (int q = tid; q < NT * 8; q += kThreads) {
+        const int c = F::col(q >> 3, (q & 7) >> 1, q & 1);
+        sm[s.wo + q] = c < w ? theta[d.w_off[d.L] + c] : 0.0;
+    }
+    if (tid == 0) sm[s.bo] = theta[d.b_off[d.L]];
+}
+
+// input fragment of layer 0 for point pt: lane t4 holds x[t4]; x[in_dim] = 1 (bias), zero beyond
+__device__ __forceinline__ double input_frag(const FragArgs& a, int64_t pt, int t4) {
+    const int in = a.d.in_dim;
+    if (t4 > in) return 0.0;
+    if (t4 == in) return 1.0;
+    if (a.X) return pt < a.n ? __ldg(a.X + pt * in + t4) : 0.0;
+    if (t4 == 0) return a.load_factor;  // [load_factor, x_c(, y_c)]: sorted dict keys of fem/properties.py:116-125
+    return pt < a.n ? __ldg(a.centroid + pt * (in - 1) + (t4 - 1)) : 0.0;
+}
+
+// offset (doubles) of hidden layer hl, m-tile mtile in a problem's activation record
+template <int KS>
+__device__ __forceinline__ int64_t acts_off(int hl, int64_t nmt, int64_t mtile) {
+    return ((int64_t)hl * nmt + mtile) * (KS * 32);
+}
+
+template <int NT, int KIND, bool SAVE>
+__global__ void __launch_bounds__(kThreads, 2) frag_forward_kernel(const __grid_constant__ FragArgs a) {
+    using F = Frag<NT, KIND>;
+    extern __shared__ __align__(16) double sm[];
+    const FragSmem& s = a.s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    const int p = blockIdx.x, L = a.d.L;
+    stage_weights<NT, KIND>(a.d, s, a.theta + (int64_t)p * a.theta_stride, sm, false);
+    __syncthreads();
+    const double* tab = sm + s.tab;
+    const int64_t nmt = a.units * 4;
+    double* acts = SAVE ? a.acts + (int64_t)p * a.acts_stride : nullptr;
+    double* dsp = SAVE ? acts + (int64_t)L * nmt * (F::KS * 32) : nullptr;
+    const int64_t u_end = min(a.units, (int64_t)(blockIdx.y + 1) * a.units_per_chunk);
+    for (int64_t unit = (int64_t)blockIdx.y * a.units_per_chunk + warp; unit < u_end; unit += kWarps) {
+        double zsel = 0.0;
+#pragma unroll 1
+        for (int mt = 0; mt < 4; ++mt) {
+            const int64_t mtile = unit * 4 + mt;
+            const double xk = input_frag(a, mtile * 8 + g, t4);
+            double act[NT][2], c[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                c[nt][0] = c[nt][1] = 0.0;
+                dmma(c[nt][0], c[nt][1], xk, sm[s.wf0 + nt * 32 + lane]);
+            }
+            for (int l = 0;; ++l) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (F::has(nt, h)) act[nt][h] = tanh_tab(c[nt][h], tab);
+                if (SAVE) {
+                    double* dst = acts + acts_off<F::KS>(l, nmt, mtile);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        if (F::has(nt, 1))
+                            *reinterpret_cast<double2*>(dst + nt * 64 + lane * 2) = make_double2(act[nt][0], act[nt][1]);
+                        else
+                            dst[nt * 64 + lane] = act[nt][0];
+                    }
+                }
+                if (l + 1 >= L) break;
+                const double* wf = sm + s.wf[l + 1] + lane;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double2 b = *reinterpret_cast<const double2*>(sm + s.bias[l + 1] + nt * 8 + t4 * 2);
+                    c[nt][0] = b.x;
+                    c[nt][1] = b.y;
+                }
+#pragma unroll
+                for (int ks = 0; ks < F::KS; ++ks)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) dmma(c[nt][0], c[nt][1], act[ks >> 1][ks & 1], wf[(ks * NT + nt) * 32]);
+            }
+            // output layer: per-lane partial dot product over the lane's slots, folded over the quad
+            double z = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double2 wo = *reinterpret_cast<const double2*>(sm + s.wo + nt * 8 + t4 * 2);
+                z = fma(wo.x, act[nt][0], z);
+                if (F::has(nt, 1)) z = fma(wo.y, act[nt][1], z);
+            }
+            z += __shfl_xor_sync(0xffffffffu, z, 1);
+            z += __shfl_xor_sync(0xffffffffu, z, 2);
+            if (t4 == mt) zsel = z;
+        }
+        // softplus for the 32 points of the unit at once: lane (g, t4) takes point 8 t4 + g
+        const double z = zsel + sm[s.bo];
+        const int64_t pt = unit * 32 + t4 * 8 + g;
+        double val = z * a.scale, dv = a.scale;
+        if (a.positive && !(z > 20.0)) {  // torch softplus: beta 1, threshold 20 (fem/properties.py:153-156)
+            const double ez = exp(z);
+            val = log1p(ez) * a.scale;
+            dv = a.scale * (ez / (1.0 + ez));
+        }
+        if (a.out && pt < a.n) a.out[pt * a.ldb + p] = val;
+        if (SAVE) dsp[unit * 32 + t4 * 8 + g] = dv;
+    }
+}
+
+// ---- transposition tile: T[point][row], 32 doubles per point, 16-byte chunks XOR-swizzled by the point ----
+__device__ __forceinline__ int t_sw(int point) { return ((point & 1) << 2) | (point & 2); }
+__device__ __forceinline__ int t_addr(int point, int row) {
+    return point * kTRows + 2 * ((row >> 1) ^ t_sw(point)) + (row & 1);
+}
+
+// write the lane's slots of a fragment (point g) into T by logical row.  ONES: the row w reads 1 (bias gradient),
+// rows beyond w read 0.
+template <int NT, int KIND, bool ONES>
+__device__ __forceinline__ void t_store(double* __restrict__ T, const double (&v)[NT][2], int g, int t4, int w) {
+    using F = Frag<NT, KIND>;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        if (F::has(nt, 1)) {
+            const int c0 = 8 * nt + 2 * t4;
+            double2 x = make_double2(v[nt][0], v[nt][1]);
+            if (ONES) {
+                if (c0 >= w) x.x = c0 == w ? 1.0 : 0.0;
+                if (c0 + 1 >= w) x.y = c0 + 1 == w ? 1.0 : 0.0;
+            }
+            *reinterpret_cast<double2*>(T + g * kTRows + 2 * ((4 * nt + t4) ^ t_sw(g))) = x;
+        } else {
+            const int c0 = 8 * nt + t4;
+            double x = v[nt][0];
+            if (ONES && c0 >= w) x = c0 == w ? 1.0 : 0.0;
+            T[t_addr(g, c0)] = x;
+        }
+    }
+}
+
+template <int L, int NT, int KIND>
+__global__ void __launch_bounds__(kThreads, 2) frag_backward_kernel(const __grid_constant__ FragArgs a) {
+    using F = Frag<NT, KIND>;
+    constexpr int KS = F::KS, NTA = F::NTA, LW = L > 1 ? L - 1 : 1;
+    extern __shared__ __align__(16) double sm[];
+    const FragSmem& s = a.s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    const int p = blockIdx.x, w = a.d.w, in_dim = a.d.in_dim;
+    stage_weights<NT, KIND>(a.d, s, a.theta + (int64_t)p * a.theta_stride, sm, true);
+    double* TD = sm + s.T + warp * 3 * kTDoubles;
+    double* TA = TD + kTDoubles;
+    double* TX = TA + kTDoubles;
+    for (int q = lane; q < 3 * kTDoubles; q += 32) TD[q] = 0.0;
+    __syncwarp();
+    if (lane < 8) TA[t_addr(lane, w)] = 1.0;  // the ones row of [a; 1] (w <= 24 < kTRows)
+    __syncthreads();
+    const int64_t nmt = a.units * 4;
+    const double* acts = a.acts + (int64_t)p * a.acts_stride;
+    const double* dsp = acts + (int64_t)L * nmt * (KS * 32);
+
+    double accW[LW][NT][NTA][2], acc0[NT][2], accO[NT][2], accbo = 0.0;
+#pragma unroll
+    for (int l = 0; l < LW; ++l)
+#pragma unroll
+        for (int mo = 0; mo < NT; ++mo)
+#pragma unroll
+            for (int ni = 0; ni < NTA; ++ni) accW[l][mo][ni][0] = accW[l][mo][ni][1] = 0.0;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc0[nt][0] = acc0[nt][1] = accO[nt][0] = accO[nt][1] = 0.0;
+
+    auto load_act = [&](int hl, int64_t mtile, double (&v)[NT][2]) {
+        const double* src = acts + acts_off<KS>(hl, nmt, mtile);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            if (F::has(nt, 1)) {
+                const double2 x = __ldcs(reinterpret_cast<const double2*>(src + nt * 64 + lane * 2));
+                v[nt][0] = x.x;
+                v[nt][1] = x.y;
+            } else {
+                v[nt][0] = __ldcs(src + nt * 64 + lane);
+                v[nt][1] = 0.0;
+            }
+        }
+    };
+
+    const int64_t mt_begin = (int64_t)blockIdx.y * a.units_per_chunk * 4;
+    const int64_t mt_end = min(a.units, (int64_t)(blockIdx.y + 1) * a.units_per_chunk) * 4;
+    for (int64_t mtile = mt_begin + warp; mtile < mt_end; mtile += kWarps) {
+        const int64_t pt = mtile * 8 + g;
+        const double xk = input_frag(a, pt, t4);
+        const double dz = pt < a.n ? __ldg(a.g_out + pt * a.ldb + p) * dsp[pt] : 0.0;
+        double act[NT][2], D[NT][2];
+        load_act(L - 1, mtile, act);
+        // output layer: dWo += dz a_L, dbo += dz;  D = wo dz (1 - a_L^2)
+        accbo += dz;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const double2 wo = *reinterpret_cast<const double2*>(sm + s.wo + nt * 8 + t4 * 2);
+            accO[nt][0] = fma(dz, act[nt][0], accO[nt][0]);
+            D[nt][0] = wo.x * dz * fma(-act[nt][0], act[nt][0], 1.0);
+            if (F::has(nt, 1)) {
+                accO[nt][1] = fma(dz, act[nt][1], accO[nt][1]);
+                D[nt][1] = wo.y * dz * fma(-act[nt][1], act[nt][1], 1.0);
+            } else {
+                D[nt][1] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int l = L - 1; l >= 1; --l) {
+            // a_l = output of hidden layer l - 1 = input of layer l
+            load_act(l - 1, mtile, act);
+            t_store<NT, KIND, false>(TD, D, g, t4, w);
+            t_store<NT, KIND, true>(TA, act, g, t4, w);
+            __syncwarp();
+            // dW_l[o][i] += sum_t D_l[o][t] a_l[i][t]  (i = w: bias)
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+                double af[NT], bf[NTA];
+#pragma unroll
+                for (int mo = 0; mo < NT; ++mo) af[mo] = TD[t_addr(k2 * 4 + t4, mo * 8 + g)];
+#pragma unroll
+                for (int ni = 0; ni < NTA; ++ni) bf[ni] = TA[t_addr(k2 * 4 + t4, ni * 8 + g)];
+#pragma unroll
+                for (int mo = 0; mo < NT; ++mo)
+#pragma unroll
+                    for (int ni = 0; ni < NTA; ++ni) dmma(accW[l - 1][mo][ni][0], accW[l - 1][mo][ni][1], af[mo], bf[ni]);
+            }
+            // back-propagate: e[t][i] = sum_o D_l[o][t] W_l[o][i];  D_{l-1} = e (1 - a_l^2)
+            double e[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) e[nt][0] = e[nt][1] = 0.0;
+            const double* wb = sm + s.wb[l] + lane;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma(e[nt][0], e[nt][1], D[ks >> 1][ks & 1], wb[(ks * NT + nt) * 32]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                D[nt][0] = e[nt][0] * fma(-act[nt][0], act[nt][0], 1.0);
+                D[nt][1] = F::has(nt, 1) ? e[nt][1] * fma(-act[nt][1], act[nt][1], 1.0) : 0.0;
+            }
+            __syncwarp();  // the tiles are rewritten below / in the next pass
+        }
+        // layer 0: dW_0[o][j] += sum_t D_0[o][t] x[j][t]  (j = in_dim: bias)
+        t_store<NT, KIND, false>(TD, D, g, t4, w);
+        TX[t_addr(g, t4)] = xk;
+        __syncwarp();
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+            const double bx = TX[t_addr(k2 * 4 + t4, g)];
+#pragma unroll
+            for (int mo = 0; mo < NT; ++mo) dmma(acc0[mo][0], acc0[mo][1], TD[t_addr(k2 * 4 + t4, mo * 8 + g)], bx);
+        }
+        __syncwarp();
+    }
+
+    // ---- fold: lanes (output layer), then warps in a fixed order, then one partial row per CTA ----
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+        accbo += __shfl_xor_sync(0xffffffffu, accbo, o);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            accO[nt][0] += __shfl_xor_sync(0xffffffffu, accO[nt][0], o);
+            accO[nt][1] += __shfl_xor_sync(0xffffffffu, accO[nt][1], o);
+        }
+    }
+    double* red = sm + s.red;
+    const PfMlpDesc& d = a.d;
+    for (int q = tid; q < d.n_params; q += kThreads) red[q] = 0.0;
+    __syncthreads();
+    for (int wv = 0; wv < kWarps; ++wv) {
+        if (warp == wv) {
+#pragma unroll
+            for (int l = 1; l < L; ++l)
+#pragma unroll
+                for (int mo = 0; mo < NT; ++mo)
+#pragma unroll
+                    for (int ni = 0; ni < NTA; ++ni)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int o = mo * 8 + g, i = ni * 8 + 2 * t4 + h;
+                            if (o < w && i < w)
+                                red[d.w_off[l] + o * w + i] += accW[l - 1][mo][ni][h];
+                            else if (o < w && i == w)
+                                red[d.b_off[l] + o] += accW[l - 1][mo][ni][h];
+                        }
+#pragma unroll
+            for (int mo = 0; mo < NT; ++mo)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int o = mo * 8 + g, j = 2 * t4 + h;
+                    if (o < w && j < in_dim)
+                        red[d.w_off[0] + o * in_dim + j] += acc0[mo][h];
+                    else if (o < w && j == in_dim)
+                        red[d.b_off[0] + o] += acc0[mo][h];
+                }
+            if (g == 0) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = F::col(nt, t4, h);
+                        if (F::has(nt, h) && c < w) red[d.w_off[L] + c] += accO[nt][h];
+                    }
+                if (t4 == 0) red[d.b_off[L]] += accbo;
+            }
+        }
+        __syncthreads();
+    }
+    double* dst = a.part + ((int64_t)p * gridDim.y + blockIdx.y) * d.n_params;
+    for (int q = tid; q < d.n_params; q += kThreads) dst[q] = red[q];
+}
+
+// g_theta[p][q] = sum over chunks of part[p][chunk][q] in chunk order
+__global__ void __launch_bounds__(256) frag_reduce_kernel(const double* __restrict__ part, int nchunks, int n_params,
+                                                          double* __restrict__ g_theta, int64_t gt_stride) {
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= n_params) return;
+    const double* src = part + (int64_t)blockIdx.y * nchunks * n_params + q;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = 0;
+    for (; c + 4 <= nchunks; c += 4) {
+        s0 += src[(int64_t)c * n_params];
+        s1 += src[(int64_t)(c + 1) * n_params];
+        s2 += src[(int64_t)(c + 2) * n_params];
+        s3 += src[(int64_t)(c + 3) * n_params];
+    }
+    for (; c < nchunks; ++c) s0 += src[(int64_t)c * n_params];
+    g_theta[(int64_t)blockIdx.y * gt_stride + q] = (s0 + s1) + (s2 + s3);
+}
+
+struct Shape {
+    int NT, kind, KS;
+};
+
+bool shape_of(const PfMlpDesc& d, Shape* sh) {
+    if (d.in_dim > 3 || d.w > 24 || d.w < 1 || d.L < 1) return false;
+    const int b = d.w % 8;
+    sh->NT = (d.w + 7) / 8;
+    sh->kind = b == 0 ? KIND_FULL : (b <= 4 ? KIND_HALF : KIND_PART);
+    sh->KS = 2 * sh->NT - (sh->kind == KIND_HALF ? 1 : 0);
+    return true;
+}
+
+int init_table() {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    PF_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return PF_OK;
+    double h[64];
+    for (int j = 0; j < 64; ++j) h[j] = exp2((double)j / 64.0);
+    PF_CUDA_CHECK(cudaMemcpyToSymbol(c_exp2_tab, h, sizeof(h)));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return PF_OK;
+}
+
+// chunks of units per problem: one wave of resident CTAs for a single problem (uniform work, fewest partial
+// gradient rows), several waves for a batch
+void chunking(int64_t units, int64_t B, int sm_count, int* nchunks, int64_t* upc) {
+    const int64_t slots = (int64_t)sm_count * 2;
+    int64_t nc = B == 1 ? slots : (slots * 8 + B - 1) / B;
+    const int64_t max_nc = (units + kWarps - 1) / kWarps;  // at least one unit per warp
+    if (nc > max_nc) nc = max_nc;
+    if (nc < 1) nc = 1;
+    *upc = (units + nc - 1) / nc;
+    *nchunks = (int)((units + *upc - 1) / *upc);
+}
+
+template <int NT, int KIND>
+int launch_fwd(const FragArgs& a, dim3 grid, size_t smem, bool save, cudaStream_t st) {
+    if (save) {
+        PF_CUDA_CHECK(cudaFuncSetAttribute(frag_forward_kernel<NT, KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frag_forward_kernel<NT, KIND, true><<<grid, kThreads, smem, st>>>(a);
+    } else {
+        PF_CUDA_CHECK(cudaFuncSetAttribute(frag_forward_kernel<NT, KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frag_forward_kernel<NT, KIND, false><<<grid, kThreads, smem, st>>>(a);
+    }
+    return PF_OK;
+}
+
+template <int L, int NT, int KIND>
+int launch_bwd(const FragArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+    PF_CUDA_CHECK(cudaFuncSetAttribute(frag_backward_kernel<L, NT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    frag_backward_kernel<L, NT, KIND><<<grid, kThreads, smem, st>>>(a);
+    return PF_OK;
+}
+
+template <int NT, int KIND>
+int launch_bwd_L(int L, const FragArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+    switch (L) {
+        case 1: return launch_bwd<1, NT, KIND>(a, grid, smem, st);
+        case 2: return launch_bwd<2, NT, KIND>(a, grid, smem, st);
+        default: return launch_bwd<3, NT, KIND>(a, grid, smem, st);
+    }
+}
+
+#define PF_FRAG_DISPATCH(SH, CALL)                                 \
+    do {                                                           \
+        const int key_ = (SH).NT * 3 + (SH).kind;                  \
+        switch (key_) {                                            \
+            case 3 + KIND_HALF: rc = CALL(1, KIND_HALF); break;    \
+            case 3 + KIND_PART: rc = CALL(1, KIND_PART); break;    \
+            case 3 + KIND_FULL: rc = CALL(1, KIND_FULL); break;    \
+            case 6 + KIND_HALF: rc = CALL(2, KIND_HALF); break;    \
+            case 6 + KIND_PART: rc = CALL(2, KIND_PART); break;    \
+            case 6 + KIND_FULL: rc = CALL(2, KIND_FULL); break;    \
+            case 9 + KIND_HALF: rc = CALL(3, KIND_HALF); break;    \
+            case 9 + KIND_PART: rc = CALL(3, KIND_PART); break;    \
+            default: rc = CALL(3, KIND_FULL); break;               \
+        }                                                          \
+    } while (0)
+
+}  // namespace
+
+bool pf_mlp_frag_supported(const PfMlpDesc& d, bool backward) {
+    Shape sh;
+    if (!shape_of(d, &sh)) return false;
+    if (backward && d.L > 3) return false;
+    if (d.L > PF_MLP_MAX_LAYERS) return false;
+    return (size_t)frag_smem(d, sh.NT, sh.KS, backward).total * sizeof(double) <= 100 * 1024;
+}
+
+int64_t pf_mlp_frag_acts_len(const PfMlpDesc& d, int64_t n) {
+    Shape sh;
+    if (!shape_of(d, &sh)) return 0;
+    const int64_t units = (n + 31) / 32;
+    return (int64_t)d.L * units * 4 * sh.KS * 32 + units * 32;
+}
+
+int pf_mlp_frag_chunks(const PfMlpDesc& d, int64_t n, int64_t B, int sm_count) {
+    int nchunks;
+    int64_t upc;
+    chunking((n + 31) / 32, B, sm_count, &nchunks, &upc);
+    return nchunks;
+}
+
+int pf_mlp_frag_forward(const PfMlpDesc& d, const double* theta, int64_t theta_stride, int64_t B, int64_t n,
+                        const double* X, const double* centroid, double load_factor, double scale, int positive,
+                        double* out, int64_t ldb, double* acts, int64_t acts_stride, int sm_count, cudaStream_t st) {
+    Shape sh;
+    PF_REQUIRE(shape_of(d, &sh), "network shape not supported by the fragment kernels");
+    if (n == 0 || B == 0) return PF_OK;
+    int rc = init_table();
+    if (rc) return rc;
+    FragArgs a{};
+    a.d = d;
+    a.theta = theta;
+    a.theta_stride = theta_stride;
+    a.n = n;
+    a.units = (n + 31) / 32;
+    a.X = X;
+    a.centroid = centroid;
+    a.load_factor = load_factor;
+    a.scale = scale;
+    a.positive = positive;
+    a.out = out;
+    a.ldb = ldb;
+    a.acts = acts;
+    a.acts_stride = acts_stride;
+    int nchunks;
+    chunking(a.units, B, sm_count, &nchunks, &a.units_per_chunk);
+    a.s = frag_smem(d, sh.NT, sh.KS, false);
+    const size_t smem = (size_t)a.s.total * sizeof(double);
+    const dim3 grid((unsigned)B, (unsigned)nchunks);
+    const bool save = acts != nullptr;
+#define PF_CALL(NTV, KV) launch_fwd<NTV, KV>(a, grid, smem, save, st)
+    PF_FRAG_DISPATCH(sh, PF_CALL);
+#undef PF_CALL
+    if (rc) return rc;
+    PF_CUDA_CHECK(cudaGetLastError());
+    return PF_OK;
+}
+
+int pf_mlp_frag_backward(const PfMlpDesc& d, const double* theta, int64_t theta_stride, int64_t B, int64_t n,
+                         const double* X, const double* centroid, double load_factor, const double* g_out, int64_t ldb,
+                         const double* acts, int64_t acts_stride, double* part, double* g_theta, int64_t gt_stride,
+                         int sm_count, cudaStream_t st) {
+    Shape sh;
+    PF_REQUIRE(shape_of(d, &sh) && d.L <= 3, "network shape not supported by the fragment kernels");
+    if (B == 0) return PF_OK;
+    int rc = init_table();
+    if (rc) return rc;
+    FragArgs a{};
+    a.d = d;
+    a.theta = theta;
+    a.theta_stride = theta_stride;
+    a.n = n;
+    a.units = (n + 31) / 32;
+    a.X = X;
+    a.centroid = centroid;
+    a.load_factor = load_factor;
+    a.ldb = ldb;
+    a.acts = const_cast<double*>(acts);
+    a.acts_stride = acts_stride;
+    a.g_out = g_out;
+    a.part = part;
+    int nchunks;
+    chunking(a.units, B, sm_count, &nchunks, &a.units_per_chunk);
+    a.s = frag_smem(d, sh.NT, sh.KS, true);
+    const size_t smem = (size_t)a.s.total * sizeof(double);
+    const dim3 grid((unsigned)B, (unsigned)nchunks);
+#define PF_CALL(NTV, KV) launch_bwd_L<NTV, KV>(d.L, a, grid, smem, st)
+    PF_FRAG_DISPATCH(sh, PF_CALL);
+#undef PF_CALL
+    if (rc) return rc;
+    frag_reduce_kernel<<<dim3((unsigned)((d.n_params + 255) / 256), (unsigned)B), 256, 0, st>>>(part, nchunks, d.n_params,
+                                                                                                g_theta, gt_stride);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return PF_OK;
+}

@@ -79,6 +79,66 @@ def mlp_backward(spec: NetSpec, theta, g_out, X=None, plan=None, load_factor=1.0
     return g_theta
 
 
+def mlp_acts_len(spec: NetSpec, n: int) -> int:
+    """Doubles per problem of the activation record the batched forward leaves for the batched backward
+    (0: the shape is not covered by the batched kernels)."""
+    return int(_lib.load().pf_mlp_acts_len(spec.input_dim, spec.hidden_layers, spec.width, int(n)))
+
+
+def _mlp_batched_args(spec: NetSpec, theta, X, plan):
+    # rows may be slices of a wider [B, n_theta_total] array (unit stride inside a row)
+    if not (isinstance(theta, torch.Tensor) and theta.is_cuda and theta.dtype == torch.float64 and theta.dim() == 2
+            and theta.shape[1] >= spec.n_params and (theta.shape[1] == 1 or theta.stride(1) == 1)):
+        raise ValueError(f"theta must be a float64 CUDA tensor [B, >= {spec.n_params}] with unit inner stride")
+    if X is None:
+        if plan is None:
+            raise ValueError("either X or a plan (element centroids) is required")
+        return theta, None, plan.nelem, plan._handle, plan.device
+    X = _dev_f64(X, "X")
+    if X.dim() != 2 or X.shape[1] != spec.input_dim:
+        raise ValueError(f"X must be [n, {spec.input_dim}]")
+    return theta, X, X.shape[0], (plan._handle if plan is not None else None), X.device
+
+
+def mlp_forward_batched(spec: NetSpec, theta, X=None, plan=None, load_factor=1.0, scale=1.0, enforce_positive=True,
+                        save_acts=True):
+    """Values of B networks (rows of ``theta`` [B, n_params]) at the same points: ``out`` [n, B] (problem index last,
+    the layout of the batched assembly kernels) and, with ``save_acts``, the activation record [B, acts_len] that
+    :func:`mlp_backward_batched` consumes."""
+    theta, X, n, handle, dev = _mlp_batched_args(spec, theta, X, plan)
+    B = theta.shape[0]
+    out = torch.empty((n, B), dtype=torch.float64, device=dev)
+    acts = None
+    if save_acts:
+        alen = mlp_acts_len(spec, n)
+        if alen <= 0:
+            raise ValueError(f"network {spec} is not covered by the batched kernels")
+        acts = torch.empty((B, alen), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().pf_mlp_forward_batched(handle, spec.input_dim, spec.hidden_layers, spec.width, _ptr(theta),
+                                                 theta.stride(0), B, n, _ptr(X), float(load_factor), float(scale),
+                                                 int(enforce_positive), _ptr(out), B, _ptr(acts), _stream_ptr(dev)))
+    return out, acts
+
+
+def mlp_backward_batched(spec: NetSpec, theta, g_out, acts, X=None, plan=None, load_factor=1.0) -> torch.Tensor:
+    """dL/dtheta [B, n_params] given dL/dvalue [n, B] and the record of :func:`mlp_forward_batched`."""
+    theta, X, n, handle, dev = _mlp_batched_args(spec, theta, X, plan)
+    B = theta.shape[0]
+    g_out = _dev_f64(g_out, "g_out")
+    acts = _dev_f64(acts, "acts")
+    if tuple(g_out.shape) != (n, B):
+        raise ValueError(f"g_out must be [{n}, {B}]")
+    if tuple(acts.shape) != (B, mlp_acts_len(spec, n)):
+        raise ValueError("acts does not match the network / point count")
+    g_theta = torch.empty((B, spec.n_params), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().pf_mlp_backward_batched(handle, spec.input_dim, spec.hidden_layers, spec.width, _ptr(theta),
+                                                  theta.stride(0), B, n, _ptr(X), float(load_factor), _ptr(g_out), B,
+                                                  _ptr(acts), _ptr(g_theta), spec.n_params, _stream_ptr(dev)))
+    return g_theta
+
+
 def mlp_param_jacobian(spec: NetSpec, theta, X=None, plan=None, load_factor=1.0, scale=1.0,
                        enforce_positive=True) -> torch.Tensor:
     """``jac[p, :] = d value_p / d theta`` for every point."""
