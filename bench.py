@@ -108,17 +108,61 @@ def algorithmic_bytes(nelem, nnode, B):
     return B * (16 * nelem + 32 * nnode) + 8 * nelem + 16 * nnode
 
 
-def synthetic_inputs(ndof, nelem, B, rank, device):
-    """This rank's shard of the synthetic batch: problems are seeded per rank (1234 + rank), so
-    shards differ between ranks and a rerun reproduces them."""
+def synthetic_problem(p, ndof, nelem):
+    """Problem p of the synthetic batch: np.random.default_rng(p), u ~ U(-1e-3, 1e-3),
+    then E, then A ~ U(0.5, 1.5)."""
+    import numpy as np
+
+    rng = np.random.default_rng(p)
+    return rng.uniform(-1e-3, 1e-3, ndof), rng.uniform(0.5, 1.5, nelem), rng.uniform(0.5, 1.5, nelem)
+
+
+def synthetic_inputs(ndof, nelem, B, first_problem, device, group=16):
+    """This rank's shard [first_problem, first_problem + B) of the synthetic batch in the kernels' layout
+    ([row][problem]): generated on the host problem by problem (a few threads), staged through pinned memory in
+    groups and transposed on the device.  f_ext is shared by all problems (default_rng(2**31))."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
     import torch
 
-    g = torch.Generator(device=device).manual_seed(1234 + rank)
-    u = (torch.rand((ndof, B), generator=g, device=device, dtype=torch.float64) - 0.5) * 2e-3
-    E = torch.rand((nelem, B), generator=g, device=device, dtype=torch.float64) + 0.5
-    A = torch.rand((nelem, B), generator=g, device=device, dtype=torch.float64) + 0.5
-    fx = torch.randn(ndof, generator=g, device=device, dtype=torch.float64) * 1e-3
+    u = torch.empty((ndof, B), dtype=torch.float64, device=device)
+    E = torch.empty((nelem, B), dtype=torch.float64, device=device)
+    A = torch.empty((nelem, B), dtype=torch.float64, device=device)
+    on_gpu = torch.device(device).type == "cuda"
+    stage = [torch.empty((group, n), dtype=torch.float64, pin_memory=on_gpu) for n in (ndof, nelem, nelem)]
+    try:
+        workers = max(1, min(8, len(os.sched_getaffinity(0))))
+    except AttributeError:
+        workers = 4
+    with ThreadPoolExecutor(workers) as pool:
+        for g0 in range(0, B, group):
+            gb = min(group, B - g0)
+            probs = list(pool.map(lambda q: synthetic_problem(first_problem + q, ndof, nelem), range(g0, g0 + gb)))
+            for j, (pu, pe, pa) in enumerate(probs):
+                stage[0][j].copy_(torch.from_numpy(pu))
+                stage[1][j].copy_(torch.from_numpy(pe))
+                stage[2][j].copy_(torch.from_numpy(pa))
+            for dst, st in zip((u, E, A), stage):
+                dst[:, g0:g0 + gb] = st[:gb].to(device, non_blocking=True).t()
+            if on_gpu:
+                torch.cuda.synchronize(device)  # the staging buffers are reused by the next group
+    fx = torch.from_numpy(np.random.default_rng(2 ** 31).normal(scale=1e-3, size=ndof)).to(device)
     return u, E, A, fx
+
+
+def oracle_parity(nodes, el, fixed, u, E, A, fx, r, cols):
+    """Columns `cols` of the device residual against the C restatement of the reference's element loop
+    (oracle/pf_oracle.c; fem/assembly.py:52-73 + fem/solver.py:267-269) on the same inputs."""
+    import numpy as np
+
+    from oracle import c_oracle
+
+    idx = list(cols)
+    uh, Eh, Ah = (np.ascontiguousarray(t[:, idx].cpu().numpy()) for t in (u, E, A))
+    _, r_ref = c_oracle.residual(nodes, el, Eh, Ah, uh, fx.cpu().numpy(), 1.0, fixed, want_f=False, want_r=True)
+    r_dev = r[:, idx].cpu().numpy()
+    return float(np.max(np.abs(r_dev - r_ref)) / np.max(np.abs(r_ref)))
 
 
 def tangent_algorithmic_bytes(nelem, nnode, nnzb, B):
@@ -247,11 +291,10 @@ def cpu_reference_leg(steps, warmup, sample_problems=None):
     threads = max(threads, c_oracle.max_threads())
     nodes, el, fixed = O.lattice_truss(NX)
     Bs = sample_problems or threads * CPU_SAMPLE_PROBLEMS_PER_THREAD
-    rng = np.random.default_rng(0)
-    u = rng.uniform(-1e-3, 1e-3, (2 * len(nodes), Bs))
-    E = rng.uniform(0.5, 1.5, (len(el), Bs))
-    A = rng.uniform(0.5, 1.5, (len(el), Bs))
-    fx = rng.normal(scale=1e-3, size=2 * len(nodes))
+    u, E, A = (np.empty((n, Bs)) for n in (2 * len(nodes), len(el), len(el)))
+    for q in range(Bs):  # the first Bs problems of the synthetic batch (same seeds as the GPU arm)
+        u[:, q], E[:, q], A[:, q] = synthetic_problem(q, 2 * len(nodes), len(el))
+    fx = np.random.default_rng(2 ** 31).normal(scale=1e-3, size=2 * len(nodes))
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -273,25 +316,57 @@ def cpu_reference_leg(steps, warmup, sample_problems=None):
             "python_loop_element_evals_per_s": py_rate, "ms_per_step": 1e3 * total / len(times)}
 
 
+def _parse_cpu_list(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
 def bind_to_gpu_numa_node(local_rank):
-    """Pin this process to the CPUs of the NUMA node its GPU hangs off, before any pinned host buffer is
-    allocated: the end-to-end leg is a host-memory -> PCIe stream and crossing sockets halves it."""
+    """Pin this process to the CPUs next to its GPU before any pinned host buffer is allocated (first touch then
+    places the buffers on that socket): the end-to-end leg is a host-memory -> PCIe stream and crossing sockets halves
+    it.  Sources, in order: sysfs numa_node of the GPU's PCI function; the CPU-affinity column of `nvidia-smi topo -m`
+    (containers often report numa_node = -1); else an even split of the allowed CPUs over the local ranks."""
+    allowed = os.sched_getaffinity(0)
     try:
         import torch
 
         p = torch.cuda.get_device_properties(local_rank)
         bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
         node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
+        if node >= 0:
+            cpus = _parse_cpu_list(Path(f"/sys/devices/system/node/node{node}/cpulist").read_text()) & allowed
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                return {"source": "sysfs", "numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    try:
+        topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        header = next(l for l in topo.splitlines() if "CPU Affinity" in l)
+        col = header.split("\t").index(next(h for h in header.split("\t") if "CPU Affinity" in h))
+        row = next(l for l in topo.splitlines() if l.startswith(f"GPU{local_rank}\t") or l.startswith(f"GPU{local_rank} "))
+        cells = [c.strip() for c in row.split("\t")]
+        cpus = _parse_cpu_list(cells[col]) & allowed
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return {"numa_node": node, "cpus": len(cpus)}
+            numa = cells[col + 1] if col + 1 < len(cells) else None
+            return {"source": "nvidia-smi topo -m", "numa_node": numa, "cpus": len(cpus)}
+    except Exception:
+        pass
+    try:
+        n_local = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        if n_local > 1:
+            ordered = sorted(allowed)
+            per = max(1, len(ordered) // n_local)
+            cpus = set(ordered[local_rank * per:(local_rank + 1) * per])
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                return {"source": "even split of the allowed CPUs over the local ranks", "numa_node": None, "cpus": len(cpus)}
     except Exception:
         pass
     return None
@@ -311,7 +386,7 @@ def main():
     out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--problems-per-gpu", type=int, default=PROBLEMS_PER_GPU)
@@ -319,6 +394,8 @@ def main():
     ap.add_argument("--e2e-problems", type=int, default=0, help="problems in the host-buffer leg (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gd", action="store_true")
+    ap.add_argument("--gd-problems-per-gpu", type=int, default=64, help="batched inverse problems per GPU (config 5)")
+    ap.add_argument("--gd-iters", type=int, default=20)
     ap.add_argument("--no-tangent", action="store_true")
     args = ap.parse_args()
 
@@ -336,10 +413,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = max(1, min(args.steps, 5))
-        base = cpu_reference_leg(steps, min(args.warmup, 1))
+        # every step is a bounded sample of the workload (8 problems per host thread x the full mesh, ~0.5 s), so
+        # --steps / --warmup are honoured as given
+        steps, warm = max(1, args.steps), max(0, args.warmup)
+        base = cpu_reference_leg(steps, warm)
         line = {"impl": "reference", "metric": "element assembly+residual evals/sec", "value": base["value"],
-                "unit": "element_evals/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+                "unit": "element_evals/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
                 "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -371,7 +450,7 @@ def main():
     nodes, el, fixed = lattice_truss(args.nx)
     plan = AssemblyPlan(nodes, el, fixed, device=dev)
     B = args.problems_per_gpu
-    u, E, A, fx = synthetic_inputs(plan.ndof, plan.nelem, B, rank, dev)
+    u, E, A, fx = synthetic_inputs(plan.ndof, plan.nelem, B, rank * B, dev)
     r = torch.empty_like(u)
 
     def barrier():
@@ -397,6 +476,14 @@ def main():
     ms_max = max_over_ranks(ms, dev)
     ms_per_step = ms_max / args.steps
     value = world * B * plan.nelem * args.steps / (ms_max * 1e-3)
+
+    # ---- parity of the benchmarked configuration itself: columns of r against the CPU oracle ----------------
+    cols = sorted({0, 1, B // 2, B - 1})
+    perr = oracle_parity(nodes, el, fixed, u, E, A, fx, r, cols)
+    perr = max_over_ranks(perr, dev)
+    parity = {"rel_err": perr, "tolerance": 1e-10, "ok": bool(perr < 1e-10), "columns_per_gpu": cols,
+              "against": "oracle/pf_oracle.c (C restatement of fem/assembly.py:52-73 + fem/solver.py:267-269), same inputs, "
+                         "full mesh; max over ranks"}
 
     # ---- roofline of the dominant (only) kernel of the step: one patch_gather launch per step -------------
     peak, peak_src = measured_peaks()
@@ -473,20 +560,28 @@ def main():
             extra["gauss_newton"] = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_gd:
         try:
-            from pinn_fem_b200.bench_gd import gd_iterations_per_second
+            from bench_gd import gd_iterations_per_second
 
             extra["pinn_gd"] = gd_iterations_per_second(dev, world)
             launches += extra["pinn_gd"].get("gpu_launches", 0)
-            from pinn_fem_b200.bench_gd import gd_large_mesh_iterations_per_second
+            from bench_gd import gd_large_mesh_iterations_per_second
 
             extra["pinn_gd_large_mesh"] = gd_large_mesh_iterations_per_second(dev, plan, world)
             launches += extra["pinn_gd_large_mesh"].pop("gpu_launches", 0)
+            from bench_gd import gd_batched_large_mesh
+
+            dmma_peak = (extra.get("gauss_newton", {}).get("fp64_peaks_measured") or {}).get("dmma_tflops")
+            del E, A, r  # the batched inverse problems need the memory of the residual batch
+            torch.cuda.empty_cache()
+            extra["pinn_gd_batched_large"] = gd_batched_large_mesh(dev, plan, world, rank, args.gd_problems_per_gpu,
+                                                                   args.gd_iters, dmma_peak)
+            launches += extra["pinn_gd_batched_large"].pop("gpu_launches", 0)
             if rank == 0:
-                from pinn_fem_b200.bench_gd import example_runs
+                from bench_gd import example_runs
 
                 extra["examples"] = example_runs(ROOT / "tests" / "golden" / "inputs")
             if world > 1:
-                from pinn_fem_b200.bench_gd import gd_element_sharded_iterations_per_second
+                from bench_gd import gd_element_sharded_iterations_per_second
 
                 extra["pinn_gd_element_sharded"] = gd_element_sharded_iterations_per_second(dev, nodes, el, fixed, world)
         except Exception as exc:  # the headline metric must not depend on the secondary one
@@ -502,8 +597,9 @@ def main():
         line = {"metric": "element assembly+residual evals/sec", "value": value, "unit": "element_evals/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic (torch.Generator seed 1234+rank: u~U(-1e-3,1e-3), E,A~U(0.5,1.5), lambda=1)",
-                "config": config, "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e,
+                "data": "synthetic (SURVEY 8d: problem p from np.random.default_rng(p): u~U(-1e-3,1e-3), E,A~U(0.5,1.5), "
+                        "lambda=1; rank k holds problems [k*B, (k+1)*B))",
+                "config": config, "roofline": roofline, "parity": parity, "cpu_baseline": cpu_base, "e2e": e2e,
                 "gpu_launches": args.steps,  # timed region: exactly one patch_gather_kernel launch per step
                 "gpu_launches_all_legs": launches, "clocks": clocks}
         line.update(extra)

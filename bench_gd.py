@@ -1,4 +1,5 @@
-"""Secondary benchmark metric: PINN-GD iterations per second (BASELINE.json configs[1]).
+"""Secondary benchmark metric: PINN-GD iterations per second (BASELINE.json configs[1] and configs[4]).
+Bench helpers (not part of the product package); imported by bench.py, scripts/ and the multi-GPU tests.
 
 Workload: the example 4-P model (4-node bar, 3 elements, E/A/rho = three tanh MLPs with
 521/316/161 parameters, 6 measured DOFs, Adam on u and theta) -- every iteration is the
@@ -10,8 +11,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import ops
-from .plan import AssemblyPlan
+from pinn_fem_b200 import ops
+from pinn_fem_b200.plan import AssemblyPlan
 
 NODES = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0], [3.0, 0.0]])
 ELEMENTS = np.array([[0, 1], [1, 2], [2, 3]])
@@ -22,7 +23,7 @@ MEAS_VALS = np.array([1.0, 0, 2, 0, 3, 0])
 
 
 def _theta0(nprob, device, seed=0):
-    from .examples.json.generic import SimpleNN
+    from pinn_fem_b200.examples.json.generic import SimpleNN
 
     torch.manual_seed(seed)
     nets = [SimpleNN(2, w, 3) for w in (20, 15, 10)]
@@ -109,13 +110,113 @@ def gd_large_mesh_iterations_per_second(device, plan, world=1, iters=100):
             "gpu_launches": 2 * iters * 12}
 
 
+def _batched_large_inputs(plan, device, B, first_problem):
+    """Problem p (global index) is seeded by p: theta_0 from torch.manual_seed(p) through the
+    reference's SimpleNN initialisation, u_0 ~ U(-1e-3, 1e-3) on the free DOFs from default_rng(p)."""
+    from pinn_fem_b200.examples.json.generic import SimpleNN
+
+    thetas, us = [], []
+    free = np.ones(plan.ndof, dtype=bool)
+    free[np.asarray(plan.fixed_dofs)] = False
+    for p in range(first_problem, first_problem + B):
+        torch.manual_seed(p)
+        nets = [SimpleNN(2, w, 3) for w in (20, 15)]
+        thetas.append(torch.cat([q.detach().reshape(-1).double() for n in nets for q in n.parameters()]))
+        us.append(np.random.default_rng(p).uniform(-1e-3, 1e-3, plan.ndof) * free)
+    return torch.stack(thetas).pin_memory(), torch.as_tensor(np.stack(us)).pin_memory()
+
+
+def gd_batched_large_mesh(device, plan, world=1, rank=0, problems_per_gpu=64, iters=20, dmma_peak_tflops=None):
+    """BASELINE.json configs[4] as stated: batched inverse problems on the 999,941-element lattice.  Every GPU
+    advances `problems_per_gpu` independent PINN-GD problems together (E and A = the 521- and 316-parameter MLPs at
+    every centroid, per-problem theta, u, Adam state): fragment MLP kernels + patch-staged residual / K r / material
+    VJP.  Also measured end to end from pinned host buffers (theta_0, u_0 in; theta, u, history out)."""
+    nets = [ops.NetSpec(3, 2, 20), ops.NetSpec(3, 2, 15), None]
+    B = problems_per_gpu
+    g = torch.Generator(device=device).manual_seed(7)
+    f_ext = torch.randn(plan.ndof, generator=g, device=device, dtype=torch.float64) * 1e-3
+    theta_h, u_h = _batched_large_inputs(plan, device, B, rank * B)
+    md = np.arange(2 * plan.nnode - 64, 2 * plan.nnode, dtype=np.int64)
+    mv_h = torch.as_tensor(np.stack([np.linspace(-1e-3, 1e-3, md.size) * (1.0 + 0.01 * p) for p in range(rank * B, rank * B + B)])).pin_memory()
+    kw = dict(tolerance=0.0, learning_rate_u=1e-5, learning_rate_theta=5e-4, alpha_physics=1.0, alpha_data=100.0,
+              load_factor=1.0)
+
+    def sync_max(x):
+        t = torch.tensor([x], device=device, dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # device-resident: the per-iteration cost is the difference of two solves of different length (removes set-up,
+    # layout changes and the reactions pass)
+    theta_d, u_d, mv_d = theta_h.to(device), u_h.to(device), mv_h.to(device)
+    ops.gd_solve(plan, nets, [1.0, 1.0, 1.0], theta_d.clone(), u_d.clone(), f_ext, md, mv_d, max_iterations=3, **kw)
+    times = {}
+    for n_it in (iters, 2 * iters):
+        th, uu = theta_d.clone(), u_d.clone()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = ops.gd_solve(plan, nets, [1.0, 1.0, 1.0], th, uu, f_ext, md, mv_d, max_iterations=n_it, **kw)
+        e1.record()
+        torch.cuda.synchronize(device)
+        times[n_it] = sync_max(e0.elapsed_time(e1))
+    assert int(res.n_iters.min()) == 2 * iters
+    ms_group_it = (times[2 * iters] - times[iters]) / iters
+    del res, th, uu
+
+    # end to end through the host-buffer entry point: pinned theta_0, u_0, targets in; theta, u, history out
+    out_theta = torch.empty_like(theta_h).pin_memory()
+    out_u = torch.empty_like(u_h).pin_memory()
+    out_hist = torch.empty((B, iters, 7), dtype=torch.float64).pin_memory()
+    torch.cuda.synchronize(device)
+    import time
+
+    t0 = time.perf_counter()
+    res = ops.gd_solve_host(plan, nets, [1.0, 1.0, 1.0], theta_h, u_h, f_ext, md, mv_h, out_theta=out_theta, out_u=out_u,
+                            out_history=out_hist, max_iterations=iters, **kw)
+    e2e_s = sync_max(time.perf_counter() - t0)
+    flops = sum(_mlp_flops(n) for n in nets[:2]) * plan.nelem  # GEMM flops of one problem-iteration (tanh not counted)
+    tfl = flops / (ms_group_it / B * 1e-3) / 1e12
+    out = {"workload": f"{plan.nelem}-element lattice x {B} inverse problems per GPU ({world * B} total), E and A = MLPs "
+                       f"(837 parameters per problem) at every centroid, 64 measured DOFs, Adam on u and theta, history "
+                       f"recorded; problem p seeded by p (theta_0: torch.manual_seed(p), u_0: default_rng(p))",
+           "dtype": "f64", "scaling": "weak", "problems_per_gpu": B,
+           "ms_per_iteration_of_the_group": ms_group_it, "ms_per_problem_iteration": ms_group_it / B,
+           "problem_iters_per_s": world * B / (ms_group_it * 1e-3),
+           "element_evals_per_s": world * B * plan.nelem / (ms_group_it * 1e-3),
+           "roofline": {"bound": "fp64 pipe (DMMA and DFMA share it)", "achieved": tfl, "unit": "TFLOP/s",
+                        "peak": dmma_peak_tflops, "frac": (tfl / dmma_peak_tflops) if dmma_peak_tflops else None,
+                        "flops_per_problem_iteration": flops,
+                        "note": "algorithmic multiply-adds of the two networks' forward and backward passes only; the 70 "
+                                "tanh per point and iteration (about half of the executed fp64 work) are not counted"},
+           "e2e_inverse": {"value": world * B * iters / e2e_s, "unit": "problem_iterations/s", "iterations": iters,
+                           "h2d_bytes_per_solve": int(theta_h.numel() + u_h.numel() + mv_h.numel()) * 8,
+                           "d2h_bytes_per_solve": int(out_theta.numel() + out_u.numel() + out_hist.numel()) * 8,
+                           "api": "ops.gd_solve_host -> pf_gd_solve (pinned host theta_0, u_0, targets in; theta, u, "
+                                  "history out; includes set-up, layout changes and the copies)",
+                           "device_resident_equivalent": world * B * iters / (times[iters] * 1e-3)},
+           "gpu_launches": 3 * 14 * iters + 14 * iters}
+    return out
+
+
+def _mlp_flops(spec):
+    """2 * MACs of forward + backward of one SimpleNN evaluation (examples/json/generic.py:118-142)."""
+    w, i = spec.width, spec.input_dim
+    fwd = i * w + (spec.hidden_layers - 1) * w * w + w
+    bwd = fwd + (spec.hidden_layers - 1) * w * w  # weight gradients of every layer + back-propagation through the hidden ones
+    return 2 * (fwd + bwd)
+
+
 def gd_element_sharded_iterations_per_second(device, nodes, elements, fixed, world, iters=100):
     """The same large-mesh PINN-GD problem as ``gd_large_mesh_iterations_per_second`` but ONE problem sharded by
     element over all ranks (strong scaling): row bands of the lattice, halo exchange of u and r with the two
     neighbours and one all-reduce of [dL/dtheta | losses] per iteration over NCCL/NVLink."""
     import torch.distributed as dist
 
-    from .element_sharding import Communicator, ShardedMesh, gd_solve_element_sharded
+    from pinn_fem_b200.element_sharding import Communicator, ShardedMesh, gd_solve_element_sharded
 
     comm = Communicator(device)
     mesh = ShardedMesh(nodes, elements, fixed, comm)
@@ -142,6 +243,18 @@ def gd_element_sharded_iterations_per_second(device, nodes, elements, fixed, wor
         if best is None or ms < best:
             best, loop_ms = ms, out["solve_ms"]
     assert out["n_iters"] == iters
+    # correctness at this rank count: the same problem through the single-GPU loop on this rank's own GPU
+    # (every rank holds the whole mesh for this check); history is replicated, u is compared on the owned rows
+    full = AssemblyPlan(nodes, elements, fixed, device=device)
+    one = ops.gd_solve(full, nets, [1.0, 1.0, 1.0], theta0[None].clone(),
+                       torch.zeros((1, 2 * nnode), dtype=torch.float64, device=device),
+                       torch.as_tensor(f_ext).to(device), md, mv, **kw)
+    relerr = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+    owned = torch.as_tensor(out["owned_dofs"]).to(device)
+    errs = torch.tensor([relerr(out["history"][:, 1:], one.history[0, :iters, 1:]), relerr(out["u_owned"], one.u[0][owned]),
+                         relerr(out["theta"], one.theta[0])], device=device, dtype=torch.float64)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    del full, one
     t = torch.tensor([best], device=device, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
@@ -152,6 +265,11 @@ def gd_element_sharded_iterations_per_second(device, nodes, elements, fixed, wor
                        f"{iters} iterations", "scaling": "strong", "dtype": "f64", "ms_per_iteration": ms / iters,
            "iters_per_s": iters / (ms * 1e-3), "loop_only_ms_per_iteration": float(t2.item()) / iters,
            "transport": comm.transport,
+           "parity_vs_single_gpu_loop": {"history_rel_err": float(errs[0]), "u_owned_rel_err": float(errs[1]),
+                                         "theta_rel_err": float(errs[2]), "tolerance": 1e-10,
+                                         "ok": bool(float(errs.max()) < 1e-10),
+                                         "what": f"{iters} iterations of the same problem on one GPU (all history columns, "
+                                                 "owned rows of u, theta), max over ranks"},
            "collectives_per_iteration": ("2 halo exchanges (one kernel each: stores into the neighbours' mailboxes over "
                                          "NVLink + epoch flag) + 1 all-reduce of 840 doubles fused into the Adam kernel"
                                          if comm.transport == "peer" else
@@ -174,8 +292,8 @@ def example_runs(golden_inputs_dir, names=("example1", "example4-P", "example7-P
     import logging
     import tempfile
 
-    from .examples.json import generic
-    from .fem import solver
+    from pinn_fem_b200.examples.json import generic
+    from pinn_fem_b200.fem import solver
 
     ref = {"example1": {"wall_s": 7.5, "note": "BASELINE.md: 7.5 s here, ~all interpreter start-up; README ~1 s"},
            "example4-P": {"wall_s": 33.8, "iterations": 1874, "iters_per_s": 55.0},

@@ -208,7 +208,10 @@ def gd_solve(plan: AssemblyPlan, nets: Sequence[Optional[NetSpec]], scales: Sequ
     n_meas = 0
     md = mv = None
     if meas_dofs is not None and meas_vals is not None and len(meas_dofs) > 0:
-        md = torch.as_tensor(meas_dofs, device=dev).to(torch.int32).contiguous()
+        md_host = torch.as_tensor(meas_dofs).cpu().to(torch.int64).reshape(-1)
+        if int(md_host.min()) < 0 or int(md_host.max()) >= plan.ndof:  # the kernels index shared / global memory with them
+            raise IndexError(f"measured DOF out of range [0, {plan.ndof}): min {int(md_host.min())}, max {int(md_host.max())}")
+        md = md_host.to(torch.int32).to(dev).contiguous()
         mv = torch.as_tensor(meas_vals, dtype=torch.float64, device=dev)
         if mv.dim() == 1:
             mv = mv.unsqueeze(0).expand(nprob, -1)
@@ -227,6 +230,33 @@ def gd_solve(plan: AssemblyPlan, nets: Sequence[Optional[NetSpec]], scales: Sequ
                                       _ptr(f_ext), _ptr(md), _ptr(mv), _ptr(history), _ptr(n_iters), _ptr(converged),
                                       _ptr(reactions), _stream_ptr(dev)))
     return GDResult(u=u, theta=theta, reactions=reactions, history=history, n_iters=n_iters, converged=converged)
+
+
+def gd_solve_host(plan: AssemblyPlan, nets, scales, theta_host, u_host, f_ext, meas_dofs=None, meas_vals_host=None, *,
+                  out_theta=None, out_u=None, out_history=None, **kw) -> GDResult:
+    """:func:`gd_solve` for problems held in (pinned) host memory -- the end-to-end form of the batched inverse
+    problem: ``theta_host`` [nprob, n_theta], ``u_host`` [nprob, ndof] and the targets go to the device, the solve
+    runs there, and theta, u and the history rows come back into ``out_theta`` / ``out_u`` / ``out_history`` (host
+    tensors, allocated pinned when not given).  The returned GDResult holds the host tensors (reactions, n_iters
+    and converged stay on the device).  Synchronous."""
+    plan._need_device()
+    dev = plan.device
+    th = theta_host.to(dev, non_blocking=True) if theta_host is not None else None
+    uu = u_host.to(dev, non_blocking=True)
+    mv = meas_vals_host.to(dev, non_blocking=True) if isinstance(meas_vals_host, torch.Tensor) else meas_vals_host
+    res = gd_solve(plan, nets, scales, th, uu, f_ext, meas_dofs, mv, **kw)
+    pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out_u = pin(res.u) if out_u is None else out_u
+    out_u.copy_(res.u, non_blocking=True)
+    if res.theta.numel():
+        out_theta = pin(res.theta) if out_theta is None else out_theta
+        out_theta.copy_(res.theta, non_blocking=True)
+    if res.history is not None:
+        out_history = pin(res.history) if out_history is None else out_history
+        out_history.copy_(res.history, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    return GDResult(u=out_u, theta=out_theta if res.theta.numel() else res.theta, reactions=res.reactions,
+                    history=out_history, n_iters=res.n_iters, converged=res.converged)
 
 
 def solve_dense(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

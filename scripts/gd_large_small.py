@@ -5,7 +5,7 @@ from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from pinn_fem_b200 import AssemblyPlan
-from pinn_fem_b200.bench_gd import gd_large_mesh_iterations_per_second
+from bench_gd import gd_large_mesh_iterations_per_second
 from pinn_fem_b200.meshes import lattice_truss
 
 ap = argparse.ArgumentParser()

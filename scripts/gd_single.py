@@ -3,7 +3,7 @@ from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from pinn_fem_b200 import ops, AssemblyPlan
-from pinn_fem_b200 import bench_gd as B
+import bench_gd as B
 dev = torch.device("cuda", 0)
 plan = AssemblyPlan(B.NODES, B.ELEMENTS, B.FIXED, device=dev)
 nets = [ops.NetSpec(3, 2, 20), ops.NetSpec(3, 2, 15), ops.NetSpec(3, 2, 10)]

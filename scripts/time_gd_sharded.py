@@ -5,7 +5,7 @@ from pathlib import Path
 import torch, torch.distributed as dist
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from pinn_fem_b200 import sharding as S
-from pinn_fem_b200.bench_gd import gd_element_sharded_iterations_per_second
+from bench_gd import gd_element_sharded_iterations_per_second
 from pinn_fem_b200.meshes import lattice_truss
 
 ap = argparse.ArgumentParser()

@@ -309,3 +309,32 @@ def test_isolated_nodes_and_empty_meshes(B):
     out = empty.residual(dev(u), z, z, dev(np.ones(10)), 2.0, r=True, half_sq=True)
     assert float(out["f_int"].abs().max()) == 0.0
     assert np.allclose(out["r"].cpu().numpy(), -2.0) and np.allclose(out["half_sq"].cpu().numpy(), 0.5 * 10 * 4.0)
+
+
+def test_benchmarked_configuration_against_the_oracle():
+    """The configuration bench.py quotes -- 578 x 578 nodes, 999,941 elements, 512 problems -- itself: columns of the
+    residual against the C restatement of the reference's element loop (fem/assembly.py:52-73, fem/solver.py:267-269)
+    on the same inputs, full mesh, 1e-10; first/last column of a chunk, chunk boundaries and the batch's last column."""
+    from oracle import c_oracle
+    from pinn_fem_b200 import AssemblyPlan
+    from pinn_fem_b200.meshes import lattice_truss
+
+    nodes, el, fixed = lattice_truss(578)
+    p = AssemblyPlan(nodes, el, fixed, device="cuda")
+    assert p.nelem == 999_941 and p.ndof == 668_168
+    B = 512
+    g = torch.Generator(device="cuda").manual_seed(11)
+    u = (torch.rand((p.ndof, B), generator=g, device="cuda", dtype=torch.float64) - 0.5) * 2e-3
+    E = torch.rand((p.nelem, B), generator=g, device="cuda", dtype=torch.float64) + 0.5
+    A = torch.rand((p.nelem, B), generator=g, device="cuda", dtype=torch.float64) + 0.5
+    fx = torch.randn(p.ndof, generator=g, device="cuda", dtype=torch.float64) * 1e-3
+    out = p.residual(u, E, A, fx, 0.8, f_int=True, r=True, half_sq=True)
+    cols = [0, 15, 16, 255, 256, 497, 511]
+    uh, Eh, Ah = (np.ascontiguousarray(t[:, cols].cpu().numpy()) for t in (u, E, A))
+    f_ref, r_ref = c_oracle.residual(nodes, el, Eh, Ah, uh, fx.cpu().numpy(), 0.8, fixed, want_f=True, want_r=True)
+    assert rel(out["f_int"][:, cols], f_ref) < TOL
+    assert rel(out["r"][:, cols], r_ref) < TOL
+    assert rel(out["half_sq"][cols], 0.5 * np.sum(r_ref * r_ref, axis=0)) < 1e-11
+    # and the C restatement itself against the numpy restatement on one column (oracle vs oracle, same algorithm)
+    f_np, _ = O.assemble_residual(nodes, el, Eh[:, :1], Ah[:, :1], uh[:, :1])
+    assert rel(f_ref[:, :1], f_np) < 1e-12

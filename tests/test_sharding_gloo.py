@@ -94,15 +94,22 @@ def test_single_process_paths_need_no_process_group():
         S.gather_problem_rows(x[:2], shard)
 
 
-def test_bench_inputs_are_rank_seeded_and_distinct():
-    """bench.py derives every rank's synthetic problems from 1234 + rank: shards differ, reruns agree."""
+def test_bench_inputs_are_seeded_per_problem():
+    """bench.py seeds problem p with np.random.default_rng(p): rank k holds problems [k B, (k+1) B), so
+    shards differ, reruns agree, and a shard does not depend on how many ranks there are."""
     import bench
 
-    a = bench.synthetic_inputs(ndof=10, nelem=7, B=4, rank=0, device="cpu")
-    b = bench.synthetic_inputs(ndof=10, nelem=7, B=4, rank=1, device="cpu")
-    a2 = bench.synthetic_inputs(ndof=10, nelem=7, B=4, rank=0, device="cpu")
+    a = bench.synthetic_inputs(ndof=10, nelem=7, B=4, first_problem=0, device="cpu", group=3)
+    b = bench.synthetic_inputs(ndof=10, nelem=7, B=4, first_problem=4, device="cpu")
+    a2 = bench.synthetic_inputs(ndof=10, nelem=7, B=4, first_problem=0, device="cpu")
     assert all(torch.equal(x, y) for x, y in zip(a, a2))
     assert not torch.equal(a[0], b[0])
+    wide = bench.synthetic_inputs(ndof=10, nelem=7, B=8, first_problem=0, device="cpu")
+    assert torch.equal(wide[0][:, 4:], b[0]) and torch.equal(wide[2][:, :4], a[2])
+    pu, pe, pa = bench.synthetic_problem(5, 10, 7)
+    assert np.array_equal(b[0][:, 1].numpy(), pu) and np.array_equal(b[1][:, 1].numpy(), pe)
+    rng = np.random.default_rng(5)
+    assert np.array_equal(pu, rng.uniform(-1e-3, 1e-3, 10)) and np.array_equal(pe, rng.uniform(0.5, 1.5, 7))
     u, E, A, fx = a
     assert u.shape == (10, 4) and E.shape == (7, 4) and fx.shape == (10,)
     assert float(u.abs().max()) <= 1e-3 and 0.5 <= float(E.min()) and float(A.max()) <= 1.5

@@ -20,7 +20,7 @@ import json, os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["PF_ROOT"])
 from pinn_fem_b200 import AssemblyPlan, ops, sharding as S
-from pinn_fem_b200 import bench_gd as B
+import bench_gd as B
 rank, local, world = S.env_rank_world()
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -77,7 +77,7 @@ def _run(tmp_path, world):
 
 def test_sharded_gd_world1_matches_direct_call(tmp_path):
     from pinn_fem_b200 import AssemblyPlan, ops
-    from pinn_fem_b200 import bench_gd as B
+    import bench_gd as B
 
     got = _run(tmp_path, 1)
     dev = torch.device("cuda", 0)
