@@ -188,6 +188,9 @@ int pf_mlp_backward_batched(pf_plan* plan, int input_dim, int hidden_layers, int
 /* y[i] = the tanh the hidden layers use (branch-free, absolute error <= 4.5e-16); exposed for its
  * accuracy test.  x, y dev [n]. */
 int pf_debug_tanh(int64_t n, const double* x, double* y, void* stream);
+/* the same for the table-based tanh of the batched / large-point-set kernels (absolute error <= 4.5e-16,
+ * +-1 from |x| = 20, NaN propagates) */
+int pf_debug_tanh_table(int64_t n, const double* x, double* y, void* stream);
 /* Jacobian rows d value_p / d theta for every point p: jac dev [n][n_params]
  * (what fem/nn_solver.py:91-110 obtains with one reverse pass per row). */
 int pf_mlp_param_jacobian(pf_plan* plan, int input_dim, int hidden_layers, int width, const double* theta,

@@ -104,6 +104,7 @@ SIGNATURES = {
     "pf_residual_host": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _vp, _dbl, _vp, _i64]),
     "pf_measure_fp64_peak": (_int, [_int, C.POINTER(_dbl)]),
     "pf_debug_tanh": (_int, [_i64, _vp, _vp, _vp]),
+    "pf_debug_tanh_table": (_int, [_i64, _vp, _vp, _vp]),
     "pf_comm_available": (_int, []),
     "pf_comm_unique_id": (_int, [_vp]),
     "pf_comm_create": (_int, [_int, _int, _vp, _int, C.POINTER(_vp)]),

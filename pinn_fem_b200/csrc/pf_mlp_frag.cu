@@ -49,32 +49,45 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// tanh with a 64-entry 2^(j/64) table (shared memory) and a degree-5 polynomial: 18 fp64 operations instead of the
-// 28 of pf_tanh, same absolute error (2.9e-16 measured over [-22, 22]); tanh(0) = 0 exactly, NaN propagates.
-__device__ __forceinline__ double tanh_tab(double x, const double* __restrict__ tab) {
-    const double ax = fabs(x);
-    const double y = ax < 20.0 ? ax + ax : 40.0;  // tanh(20) rounds to 1
-    const double shifter = 6755399441055744.0;    // 1.5 * 2^52
-    const double t = fma(y, 1.4426950408889634 * 64.0, shifter);
+// tanh with a 64-entry 2^(j/64) table (shared memory) and a degree-5 polynomial.  The forward kernel is bound by
+// the fp64 pipe AND close to its instruction-issue limit, so the common case carries nothing else: 16 fp64 operations
+// (pf_tanh: 28) + ~9 integer / load instructions; the factor 2 of exp(2|x|) is folded into the constants and |x| is an
+// operand modifier.  Absolute error 2.9e-16 (measured over [-22, 22]), tanh(0) = 0 exactly.
+//   tanh(x) = sign(x) (1 - 2 / (exp(2|x|) + 1)),  2|x| = n ln2/64 + r,  exp(2|x|) = 2^(n>>6) tab[n&63] exp(r)
+// tanh_core is valid for |x| < 20 only; tanh_fix patches |x| >= 20 (+-1), infinities and NaNs (propagated) and is
+// called behind ONE warp-level test per batch of evaluations (tanh_any_big), so it is almost never executed.
+__device__ __forceinline__ double tanh_core(double x, const double* __restrict__ tab) {
+    const double shifter = 6755399441055744.0;  // 1.5 * 2^52: rint lands in the low word
+    const double t = fma(fabs(x), 2.0 * 64.0 * 1.4426950408889634, shifter);
     const int n = __double2loint(t);
     const double nf = t - shifter;
-    double r = fma(nf, -6.93147180369123816490e-01 / 64.0, y);
-    r = fma(nf, -1.90821492927058770002e-10 / 64.0, r);
-    double p = fma(r, 8.333333333333333e-03, 4.1666666666666664e-02);  // exp(r), |r| <= ln2 / 128
-    p = fma(p, r, 1.6666666666666666e-01);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    double h = fma(nf, -6.93147180369123816490e-01 / 128.0, fabs(x));  // h = r / 2, |h| <= ln2 / 256
+    h = fma(nf, -1.90821492927058770002e-10 / 128.0, h);
+    double p = fma(h, 32.0 / 120.0, 16.0 / 24.0);  // exp(2h) = sum (2h)^k / k!, degree 5
+    p = fma(p, h, 8.0 / 6.0);
+    p = fma(p, h, 2.0);
+    p = fma(p, h, 2.0);
+    p = fma(p, h, 1.0);
     p *= tab[n & 63];
-    const double e = __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));  // p * 2^(n / 64)
+    const double e = __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));  // p * 2^(n >> 6)
     const double d = e + 1.0;
     double q;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(d));
-    q = fma(q, fma(-d, q, 1.0), q);
+    q = fma(q, fma(-d, q, 1.0), q);  // two Newton steps: 2^-20 -> 2^-40 -> full precision
     q = fma(q, fma(-d, q, 1.0), q);
     const double res = fma(-2.0, q, 1.0);
-    return x != x ? x : copysign(res, x);
+    return __hiloint2double(__double2hiint(res) | (__double2hiint(x) & 0x80000000), __double2loint(res));
 }
+// high word of |x| (monotone in |x|; NaNs and infinities are the largest values)
+__device__ __forceinline__ int tanh_mag(double x) { return __double2hiint(x) & 0x7fffffff; }
+constexpr int kTanhBig = 0x40340000;  // high word of 20.0
+__device__ __forceinline__ double tanh_fix(double x, double y) {
+    const int hi = tanh_mag(x);
+    if (hi < kTanhBig) return y;
+    const bool nan = hi > 0x7ff00000 || (hi == 0x7ff00000 && __double2loint(x) != 0);
+    return nan ? x : copysign(1.0, x);  // tanh(20) rounds to 1
+}
+__device__ __forceinline__ double tanh_tab(double x, const double* __restrict__ tab) { return tanh_fix(x, tanh_core(x, tab)); }
 
 // Column slots of a w-wide activation in fragment order.  Lane (g = lane / 4, t4 = lane % 4) holds, for point g of
 // the m-tile, the slots (nt, h): nt < NT n-tiles, h < 2.  Logical column of a slot: 8 nt + 2 t4 + h, except in the
@@ -211,8 +224,14 @@ __device__ __forceinline__ int64_t acts_off(int hl, int64_t nmt, int64_t mtile) 
     return ((int64_t)hl * nmt + mtile) * (KS * 32);
 }
 
+#ifndef PF_FRAG_FWD_MINB
+#define PF_FRAG_FWD_MINB 2
+#endif
+#ifndef PF_FRAG_BWD_MINB
+#define PF_FRAG_BWD_MINB 2
+#endif
 template <int NT, int KIND, bool SAVE>
-__global__ void __launch_bounds__(kThreads, 2) frag_forward_kernel(const __grid_constant__ FragArgs a) {
+__global__ void __launch_bounds__(kThreads, PF_FRAG_FWD_MINB) frag_forward_kernel(const __grid_constant__ FragArgs a) {
     using F = Frag<NT, KIND>;
     extern __shared__ __align__(16) double sm[];
     const FragSmem& s = a.s;
@@ -225,12 +244,15 @@ __global__ void __launch_bounds__(kThreads, 2) frag_forward_kernel(const __grid_
     double* acts = SAVE ? a.acts + (int64_t)p * a.acts_stride : nullptr;
     double* dsp = SAVE ? acts + (int64_t)L * nmt * (F::KS * 32) : nullptr;
     const int64_t u_end = min(a.units, (int64_t)(blockIdx.y + 1) * a.units_per_chunk);
+    double xnext = input_frag(a, ((int64_t)blockIdx.y * a.units_per_chunk + warp) * 32 + g, t4);
     for (int64_t unit = (int64_t)blockIdx.y * a.units_per_chunk + warp; unit < u_end; unit += kWarps) {
         double zsel = 0.0;
 #pragma unroll 1
         for (int mt = 0; mt < 4; ++mt) {
             const int64_t mtile = unit * 4 + mt;
-            const double xk = input_frag(a, mtile * 8 + g, t4);
+            const double xk = xnext;
+            // the next m-tile's inputs (of this unit, then of the warp's next unit) travel while this one computes
+            xnext = input_frag(a, (mt < 3 ? mtile + 1 : (unit + kWarps) * 4) * 8 + g, t4);
             double act[NT][2], c[NT][2];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
@@ -238,11 +260,22 @@ __global__ void __launch_bounds__(kThreads, 2) frag_forward_kernel(const __grid_
                 dmma(c[nt][0], c[nt][1], xk, sm[s.wf0 + nt * 32 + lane]);
             }
             for (int l = 0;; ++l) {
+                int mag = 0;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
-                        if (F::has(nt, h)) act[nt][h] = tanh_tab(c[nt][h], tab);
+                        if (F::has(nt, h)) {
+                            act[nt][h] = tanh_core(c[nt][h], tab);
+                            mag = max(mag, tanh_mag(c[nt][h]));
+                        }
+                if (mag >= kTanhBig) {  // rare: some |pre-activation| >= 20, an infinity or a NaN
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            if (F::has(nt, h)) act[nt][h] = tanh_fix(c[nt][h], act[nt][h]);
+                }
                 if (SAVE) {
                     double* dst = acts + acts_off<F::KS>(l, nmt, mtile);
 #pragma unroll
@@ -323,7 +356,7 @@ __device__ __forceinline__ void t_store(double* __restrict__ T, const double (&v
 }
 
 template <int L, int NT, int KIND>
-__global__ void __launch_bounds__(kThreads, 2) frag_backward_kernel(const __grid_constant__ FragArgs a) {
+__global__ void __launch_bounds__(kThreads, PF_FRAG_BWD_MINB) frag_backward_kernel(const __grid_constant__ FragArgs a) {
     using F = Frag<NT, KIND>;
     constexpr int KS = F::KS, NTA = F::NTA, LW = L > 1 ? L - 1 : 1;
     extern __shared__ __align__(16) double sm[];
@@ -367,12 +400,32 @@ __global__ void __launch_bounds__(kThreads, 2) frag_backward_kernel(const __grid
         }
     };
 
+    // the warp's next m-tile is pulled into L2 while this one computes (the loads then cost an L2 hit, not HBM)
+    auto prefetch_tile = [&](int64_t mtile) {
+#pragma unroll
+        for (int hl = 0; hl < L; ++hl) {
+            const double* src = acts + acts_off<KS>(hl, nmt, mtile);
+#pragma unroll
+            for (int q = 0; q < (KS * 32 * 8 + 1023) / 1024; ++q)  // 32 lanes x 32-byte sectors per instruction
+                if (q * 128 + lane * 4 < KS * 32)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + q * 128 + lane * 4));
+        }
+    };
+
     const int64_t mt_begin = (int64_t)blockIdx.y * a.units_per_chunk * 4;
     const int64_t mt_end = min(a.units, (int64_t)(blockIdx.y + 1) * a.units_per_chunk) * 4;
-    for (int64_t mtile = mt_begin + warp; mtile < mt_end; mtile += kWarps) {
+    // dL/dz and the input fragment of the warp's NEXT m-tile are loaded into registers one iteration ahead (the
+    // strided g_out column is the longest-latency load of the loop: 30 % of the warp samples stalled on it before)
+    auto load_dz = [&](int64_t mtile) {
         const int64_t pt = mtile * 8 + g;
-        const double xk = input_frag(a, pt, t4);
-        const double dz = pt < a.n ? __ldg(a.g_out + pt * a.ldb + p) * dsp[pt] : 0.0;
+        return pt < a.n ? __ldg(a.g_out + pt * a.ldb + p) * dsp[pt] : 0.0;
+    };
+    double dz_next = load_dz(mt_begin + warp), x_next = input_frag(a, (mt_begin + warp) * 8 + g, t4);
+    for (int64_t mtile = mt_begin + warp; mtile < mt_end; mtile += kWarps) {
+        if (mtile + kWarps < mt_end) prefetch_tile(mtile + kWarps);
+        const double xk = x_next, dz = dz_next;
+        dz_next = load_dz(mtile + kWarps);  // beyond the chunk: points of the next chunk or >= n (then 0); never used
+        x_next = input_frag(a, (mtile + kWarps) * 8 + g, t4);
         double act[NT][2], D[NT][2];
         load_act(L - 1, mtile, act);
         // output layer: dWo += dz a_L, dbo += dz;  D = wo dz (1 - a_L^2)
@@ -543,7 +596,7 @@ int init_table() {
 // chunks of units per problem: one wave of resident CTAs for a single problem (uniform work, fewest partial
 // gradient rows), several waves for a batch
 void chunking(int64_t units, int64_t B, int sm_count, int* nchunks, int64_t* upc) {
-    const int64_t slots = (int64_t)sm_count * 2;
+    const int64_t slots = (int64_t)sm_count * (PF_FRAG_FWD_MINB > PF_FRAG_BWD_MINB ? PF_FRAG_FWD_MINB : PF_FRAG_BWD_MINB);
     int64_t nc = B == 1 ? slots : (slots * 8 + B - 1) / B;
     const int64_t max_nc = (units + kWarps - 1) / kWarps;  // at least one unit per warp
     if (nc > max_nc) nc = max_nc;
@@ -596,7 +649,26 @@ int launch_bwd_L(int L, const FragArgs& a, dim3 grid, size_t smem, cudaStream_t 
         }                                                          \
     } while (0)
 
+__global__ void tanh_tab_probe_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ y) {
+    __shared__ double tab[64];
+    if (threadIdx.x < 64) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = tanh_tab(x[i], tab);
+}
+
 }  // namespace
+
+// y[i] = the table-based tanh of the fragment kernels (dev pointers), exposed for its accuracy test
+extern "C" int pf_debug_tanh_table(int64_t n, const double* x, double* y, void* stream) {
+    PF_REQUIRE(n >= 0 && (n == 0 || (x && y)), "pf_debug_tanh_table: bad argument");
+    if (n == 0) return PF_OK;
+    int rc = init_table();
+    if (rc) return rc;
+    tanh_tab_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pf_stream_of(stream)>>>(n, x, y);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return PF_OK;
+}
 
 bool pf_mlp_frag_supported(const PfMlpDesc& d, bool backward) {
     Shape sh;

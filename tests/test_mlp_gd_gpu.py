@@ -342,9 +342,10 @@ def test_gd_large_mesh_graph_replay_equals_eager(monkeypatch):
             assert int(out["0"].n_iters[0]) == 12
 
 
-def test_hidden_layer_tanh_accuracy():
-    """The branch-free tanh of the MLP kernels: absolute error <= 4.5e-16 over the whole range, exact limits,
-    odd symmetry, NaN propagation."""
+@pytest.mark.parametrize("entry", ["pf_debug_tanh", "pf_debug_tanh_table"])
+def test_hidden_layer_tanh_accuracy(entry):
+    """The tanh of the MLP kernels (branch-free Estrin version; table-based version of the fragment kernels):
+    absolute error <= 4.5e-16 over the whole range, exact limits, odd symmetry, NaN propagation."""
     import ctypes as C
 
     from pinn_fem_b200 import _lib
@@ -355,7 +356,7 @@ def test_hidden_layer_tanh_accuracy():
                                                          np.inf, -np.inf, np.nan]])
     xd = dev(x)
     yd = torch.empty_like(xd)
-    _lib.check(_lib.load().pf_debug_tanh(x.size, C.c_void_p(xd.data_ptr()), C.c_void_p(yd.data_ptr()),
+    _lib.check(getattr(_lib.load(), entry)(x.size, C.c_void_p(xd.data_ptr()), C.c_void_p(yd.data_ptr()),
                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     y = yd.cpu().numpy()
     ref = np.tanh(x)
@@ -366,6 +367,6 @@ def test_hidden_layer_tanh_accuracy():
     xs = np.abs(x[ok])
     ys = dev(xs)
     ym = torch.empty_like(ys)
-    _lib.check(_lib.load().pf_debug_tanh(xs.size, C.c_void_p(ys.data_ptr()), C.c_void_p(ym.data_ptr()),
+    _lib.check(getattr(_lib.load(), entry)(xs.size, C.c_void_p(ys.data_ptr()), C.c_void_p(ym.data_ptr()),
                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     assert np.array_equal(np.abs(y[ok]), ym.cpu().numpy())  # odd
