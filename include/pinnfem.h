@@ -345,6 +345,16 @@ int64_t pf_cg_work_len(const pf_plan* plan, int64_t B);
 int pf_gn_normal_equations(int64_t m, int64_t n, const double* J, const double* R, double damping_factor,
                            double* jtj, double* jtr, double* damping_out, void* stream);
 
+/* One damped Gauss-Newton / Levenberg-Marquardt step (fem/nn_solver.py:266-277):
+ *   dx = -(J^T J + d I)^-1 J^T R,  d = damping_factor * trace(J^T J) / n.
+ * With fewer residuals than unknowns (m < n: every inverse problem of the reference, 6 x 1001 on example 10) the
+ * step is taken through the m x m dual system (J J^T + d I) y = R, dx = -J^T y -- the same vector, O(m^2 n) work
+ * instead of O(n^3).  path: 0 = choose, 1 = force the n x n system, 2 = force the dual.  J dev [m][n] row-major,
+ * R dev [m], dx dev [n] out, damping_out dev [1] out (may be NULL), info dev int32 [1] (pivot report of
+ * pf_solve_spd). */
+int pf_gn_lm_step(int64_t m, int64_t n, const double* J, const double* R, double damping_factor, int path, double* dx,
+                  double* damping_out, int32_t* info, void* stream);
+
 /* Stacked Gauss-Newton Jacobian (fem/nn_solver.py:50-135, :223-239), dense row-major
  *   J dev [(nfree + n_meas)][nfree + nE + nA + n_rest]:
  *     rows 0..nfree-1     [ alpha_physics*K_ff | alpha_physics*d f_int[free]/d theta ]

@@ -829,6 +829,17 @@ def lm_step(J, R):
     return np.linalg.solve(reg, -jtr), jtj, jtr, damping
 
 
+def lm_step_dual(J, R):
+    """The same step through the m x m dual system: ``(J^T J + d I)^-1 J^T = J^T (J J^T + d I)^-1`` with the
+    reference's damping ``d = 1e-6 tr(J^T J)/n`` (= 1e-6 tr(J J^T)/n).  Identical in exact arithmetic; the n x n
+    matrix is a rank-m matrix plus a 1e-6-relative ridge (condition ~1e6 n/m and worse), so the two agree only as
+    far as that conditioning allows."""
+    g = J @ J.T
+    damping = 1e-6 * np.trace(g) / J.shape[1]
+    y = np.linalg.solve(g + damping * np.eye(g.shape[0], dtype=J.dtype), R)
+    return -(J.T @ y), damping
+
+
 def _theta_add(mat: MaterialNets, delta, step):
     off = 0
     for _, (spec, theta, _s) in mat.nets():
@@ -838,9 +849,10 @@ def _theta_add(mat: MaterialNets, delta, step):
 
 def solve_pinn_newton_raphson(mesh: Mesh, mat: MaterialNets, f_ext, meas_vals=None, meas_dofs=None,
                               max_iterations=50, tolerance=1e-6, alpha_p=1.0, alpha_d=1.0,
-                              min_denominator=1e-12, line_search=True, kind=LINEAR, dtype=np.float64):
+                              min_denominator=1e-12, line_search=True, kind=LINEAR, dtype=np.float64, dual=False):
     """fem/nn_solver.py:138-426 including its quirks: on an accepted trial
-    theta keeps the trial update and is advanced again (:309-313 + :366-371)."""
+    theta keeps the trial update and is advanced again (:309-313 + :366-371).  ``dual``: take the LM step through
+    :func:`lm_step_dual` (what the CUDA path does when there are fewer residuals than unknowns)."""
     free, fixed = free_and_fixed_dofs(mesh.ndof, mesh.fixed_dofs)
     u = np.zeros(mesh.ndof, dtype=dtype)
     f_ext = np.asarray(f_ext, dtype=dtype)
@@ -866,7 +878,7 @@ def solve_pinn_newton_raphson(mesh: Mesh, mat: MaterialNets, f_ext, meas_vals=No
         rp_n, rd_n, rt_n = (float(np.linalg.norm(r_p)), float(np.linalg.norm(r_d)) if has_meas else 0.0,
                             float(np.linalg.norm(R)))
         try:
-            dx, _, _, _ = lm_step(J, R)
+            dx = lm_step_dual(J, R)[0] if dual else lm_step(J, R)[0]
         except np.linalg.LinAlgError:
             break
         du_f, dth = dx[:n_free], dx[n_free:]

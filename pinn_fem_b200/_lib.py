@@ -100,6 +100,7 @@ SIGNATURES = {
     "pf_cg_solve": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _int, _vp, _vp, _dbl, _int, _vp, _i64, _vp, _vp, _vp]),
     "pf_cg_work_len": (_i64, [_vp, _i64]),
     "pf_gn_normal_equations": (_int, [_i64, _i64, _vp, _vp, _dbl, _vp, _vp, _vp, _vp]),
+    "pf_gn_lm_step": (_int, [_i64, _i64, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _vp]),
     "pf_gn_jacobian": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _dbl, _dbl, _vp, _i64, _vp, _vp]),
     "pf_residual_host": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _vp, _dbl, _vp, _i64]),
     "pf_measure_fp64_peak": (_int, [_int, C.POINTER(_dbl)]),

@@ -264,3 +264,68 @@ extern "C" int pf_gn_jacobian(pf_plan* plan, int kind, const double* u, const do
     PF_CUDA_CHECK(cudaGetLastError());
     return PF_OK;
 }
+
+namespace {
+__global__ void transpose_small_kernel(int64_t m, int64_t n, const double* __restrict__ J, double* __restrict__ Jt) {
+    __shared__ double t[32][33];
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    if (r0 + threadIdx.y < m && c0 + threadIdx.x < n) t[threadIdx.y][threadIdx.x] = J[(r0 + threadIdx.y) * n + c0 + threadIdx.x];
+    __syncthreads();
+    if (c0 + threadIdx.y < n && r0 + threadIdx.x < m) Jt[(c0 + threadIdx.y) * m + r0 + threadIdx.x] = t[threadIdx.x][threadIdx.y];
+}
+// dx[c] = -sum_i J[i][c] y[i] (ascending i: fixed order)
+__global__ void neg_jt_times_kernel(int64_t m, int64_t n, const double* __restrict__ J, const double* __restrict__ y,
+                                    double* __restrict__ dx) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double acc = 0.0;
+    for (int64_t i = 0; i < m; ++i) acc = fma(J[i * n + c], y[i], acc);
+    dx[c] = -acc;
+}
+__global__ void negate_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = -x[i];
+}
+}  // namespace
+
+// One Levenberg-Marquardt step dx = -(J^T J + d I)^-1 J^T R, d = damping_factor * trace(J^T J) / n
+// (fem/nn_solver.py:266-277).  The inverse problems of this code base have far fewer residuals than unknowns
+// (6 x 1001 on example 10): then the step is taken through the m x m dual system
+//     (J J^T + d I) y = R,   dx = -J^T y            [(J^T J + d I)^-1 J^T = J^T (J J^T + d I)^-1]
+// which costs O(m^2 n) instead of O(n^3) and is better conditioned (the n x n matrix is J^T J plus a 1e-6-relative
+// ridge on an (n - m)-dimensional null space).  path: 0 = choose (dual when m < n), 1 = n x n system, 2 = dual.
+extern "C" int pf_gn_lm_step(int64_t m, int64_t n, const double* J, const double* R, double damping_factor, int path,
+                             double* dx, double* damping_out, int32_t* info, void* stream) {
+    PF_REQUIRE(m >= 1 && n >= 1 && J && R && dx && info, "pf_gn_lm_step: bad argument");
+    PF_REQUIRE(path >= 0 && path <= 2, "pf_gn_lm_step: path must be 0, 1 or 2");
+    cudaStream_t st = pf_stream_of(stream);
+    pf_keep_pool_cached();
+    const bool dual = path == 2 || (path == 0 && m < n);
+    double* work = nullptr;
+    int rc = PF_OK;
+    if (dual) {
+        PF_CUDA_CHECK(cudaMallocAsync((void**)&work, (size_t)(n * m + m * m + m) * sizeof(double), st));
+        double *Jt = work, *G = Jt + n * m, *y = G + m * m;
+        transpose_small_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32)), dim3(32, 32), 0, st>>>(m, n, J, Jt);
+        // Gram matrix of the rows = (J^T)^T (J^T); its trace equals trace(J^T J), the ridge is rescaled to the n unknowns
+        rc = pf_gn_normal_equations(n, m, Jt, nullptr, damping_factor * (double)m / (double)n, G, nullptr, damping_out, stream);
+        if (!rc) {
+            cudaMemcpyAsync(y, R, m * sizeof(double), cudaMemcpyDeviceToDevice, st);
+            rc = pf_solve_spd(m, G, y, info, stream);
+        }
+        if (!rc) neg_jt_times_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m, n, J, y, dx);
+    } else {
+        PF_CUDA_CHECK(cudaMallocAsync((void**)&work, (size_t)(n * n + n) * sizeof(double), st));
+        double *jtj = work, *jtr = jtj + n * n;
+        rc = pf_gn_normal_equations(m, n, J, R, damping_factor, jtj, jtr, damping_out, stream);
+        if (!rc) {
+            negate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, jtr, dx);
+            rc = pf_solve_spd(n, jtj, dx, info, stream);
+        }
+    }
+    const cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(work, st);
+    if (rc) return rc;
+    PF_CUDA_CHECK(le);
+    return PF_OK;
+}

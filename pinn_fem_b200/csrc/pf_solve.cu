@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) lu_small_kernel(int n, double* __restrict
             warp_argmax(best, bi);
             if (tid == 0) {
                 s_piv = bi;
-                if (best == 0.0 && s_info == 0) s_info = k + 1;
+                if (!(best > 0.0) && s_info == 0) s_info = k + 1;  // zero column, or nothing but NaNs (best stays -1)
             }
         }
         __syncthreads();
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(1024) lu_panel_kernel(int n, int k0, int nb, d
             if (lane == 0) {
                 s_p = bi;
                 piv[j] = bi;
-                if (best == 0.0 && *info == 0) *info = col + 1;
+                if (!(best > 0.0) && *info == 0) *info = col + 1;  // zero column, or nothing but NaNs (best stays -1)
             }
         }
         __syncthreads();
@@ -237,9 +237,14 @@ __global__ void __cluster_dims__(kLuCluster, 1, 1) __launch_bounds__(1024)
                 p = i;
             }
         }
+        // every remaining entry of the column is NaN: no candidate ever compares greater, all CTAs publish
+        // (-1, INT_MAX).  Keep row `col` as the pivot (an in-range owner for the DSMEM reads below) and report the
+        // column as singular, like a zero pivot: the host raises the reference's error instead of the GPU faulting.
+        const bool no_pivot = p == INT_MAX;
+        if (no_pivot) p = col;
         if (rank == 0 && tid == 0) {
             piv[j] = p;
-            if (gb == 0.0 && *info == 0) *info = col + 1;
+            if ((gb == 0.0 || no_pivot) && *info == 0) *info = col + 1;
         }
         const int op = (p - k0) / rows_per, oc = (col - k0) / rows_per;  // owners of the pivot row and of row `col`
         if (tid < nb) {  // everyone needs the pivot row; its owner also needs the row it trades places with

@@ -91,12 +91,30 @@ def compute_jacobian_blocks(model: FEMModel, u: torch.Tensor, f_ext_torch: torch
     return J[:nf, :nf].clone(), J[:nf, nf:].clone(), r[free], j_data_u, None
 
 
-def _gauss_newton(model, f_ext, measured_disp, measured_dofs, config, load_factor=1.0):
+def _line_search_steps(n=15):
+    """The step sizes the reference's backtracking loop visits (nn_solver.py:293-355): 1, then `step *= 0.7` per
+    rejected trial, as the same fp64 products; entry n is the step it is left with when all n trials fail."""
+    steps, step = [], 1.0
+    for _ in range(n + 1):
+        steps.append(step)
+        step *= 0.7
+    return steps
+
+
+def _gauss_newton(model, f_ext, measured_disp, measured_dofs, config, load_factor=1.0, lm_path="auto"):
+    """fem/nn_solver.py:223-371 with the iteration resident on the device: residual, closed-form Jacobian, the
+    Levenberg-Marquardt step (dual m x m system when there are fewer residuals than unknowns), and the backtracking
+    line search evaluated for ALL 15 trial steps at once (one batched network forward + one batched residual; the
+    first step that passes the sufficient-decrease test is selected on the device, which is what the sequential loop
+    would have stopped at).  The host reads one small record per iteration (norms, step, solver status)."""
+    import os
+
+    if lm_path == "auto":  # PF_GN_LM_PATH=primal|dual forces one formulation (tests compare the two)
+        lm_path = os.environ.get("PF_GN_LM_PATH", "auto")
     st = _State(model, load_factor)
     plan, dev = st.plan, st.dev
     f_ext_d = to_dev(f_ext, dev)
     free = torch.as_tensor(plan.free_dofs.copy(), device=dev)
-    fixed = torch.as_tensor(plan.fixed_dofs.copy(), device=dev)
     nf = plan.nfree
     has_meas = measured_disp is not None and measured_dofs is not None
     md_np = np.asarray(measured_dofs, dtype=np.int64) if has_meas else None
@@ -105,15 +123,39 @@ def _gauss_newton(model, f_ext, measured_disp, measured_dofs, config, load_facto
     u = torch.zeros(plan.ndof, dtype=torch.float64, device=dev)
     ap, ad = float(config.alpha_physics), float(config.alpha_data)
     history, converged = [], False
+    n_trials = 15
+    steps = torch.tensor(_line_search_steps(n_trials), dtype=torch.float64, device=dev)
+    trial_steps = steps[:n_trials]
+    nets = {name: getattr(model.material, name) for name in ("young", "area")}
+    free_mask = torch.zeros(plan.ndof, dtype=torch.float64, device=dev)
+    free_mask[free] = 1.0
 
-    def residual_parts(uu):
-        E, A = st.field("young"), st.field("area")
-        r_p = (plan.internal_force(uu, E, A) - f_ext_d)[free]
-        r_d = (mv - uu[md]) if has_meas else torch.zeros(0, dtype=torch.float64, device=dev)
-        return E, A, r_p, r_d
+    def trial_fields(theta_rows):
+        """E, A [nelem, n_trials] for the rows of trial parameter vectors."""
+        out = []
+        for name in ("young", "area"):
+            prop = nets[name]
+            if isinstance(prop, NNProperty):
+                o, n = st.offsets[name]
+                if ops.mlp_acts_len(prop.spec, plan.nelem) > 0:
+                    vals, _ = ops.mlp_forward_batched(prop.spec, theta_rows[:, o:], plan=plan, load_factor=st.lam,
+                                                      scale=prop.scale, enforce_positive=prop.enforce_positive,
+                                                      save_acts=False)
+                else:  # shapes outside the batched kernels: one launch per trial
+                    vals = torch.stack([ops.mlp_forward(prop.spec, theta_rows[k, o:o + n].contiguous(), plan=plan,
+                                                        load_factor=st.lam, scale=prop.scale,
+                                                        enforce_positive=prop.enforce_positive)
+                                        for k in range(theta_rows.shape[0])], dim=1).contiguous()
+            else:
+                vals = torch.full((plan.nelem, theta_rows.shape[0]), float(prop.value()), dtype=torch.float64, device=dev)
+            out.append(vals)
+        return out
 
     for it in range(int(config.max_iterations)):
-        E, A, r_p, r_d = residual_parts(u)
+        E, A = st.field("young"), st.field("area")
+        r_full = (plan.internal_force(u, E, A) - f_ext_d)
+        r_p = r_full[free]
+        r_d = (mv - u[md]) if has_meas else torch.zeros(0, dtype=torch.float64, device=dev)
         jE, jA = st.param_jacobian("young"), st.param_jacobian("area")
         n_rest = st.n_theta - (0 if jE is None else jE.shape[1]) - (0 if jA is None else jA.shape[1])
         if has_meas:
@@ -122,45 +164,48 @@ def _gauss_newton(model, f_ext, measured_disp, measured_dofs, config, load_facto
         else:  # the reference leaves J unweighted here and scales only R (nn_solver.py:240-243)
             J = ops.gn_jacobian(plan, u, E, A, jE, jA, n_rest=n_rest, alpha_physics=1.0, alpha_data=1.0)
             R = ap * r_p
-        rp_n, rd_n, rt_n = float(torch.linalg.vector_norm(r_p)), float(torch.linalg.vector_norm(r_d)), float(torch.linalg.vector_norm(R))
-        jtj, jtr, _ = ops.gn_normal_equations(J, R.contiguous(), 1e-6)
-        try:
-            dx = ops.solve_spd(jtj, (-jtr).contiguous())  # J^T J + d I is SPD: Cholesky (the reference's LU agrees to rounding)
-        except RuntimeError as exc:
-            print(f"Solver failed at iteration {it + 1}: {exc}")
-            break
-        du_f, dth = dx[:nf], dx[nf:]
-        step = 1.0
+        rp_n, rd_n, rt_n = torch.linalg.vector_norm(r_p), torch.linalg.vector_norm(r_d), torch.linalg.vector_norm(R)
+        # (J^T J + d I) dx = -J^T R is SPD by construction (the reference's LU agrees to rounding)
+        dx, _, info = ops.gn_lm_step(J, R.contiguous(), 1e-6, path=lm_path, check_info=False)
+        du = torch.zeros(plan.ndof, dtype=torch.float64, device=dev)
+        du[free] = dx[:nf]
+        dth = dx[nf:]
         if config.line_search:
-            for _ in range(15):
-                u_t = u.clone()
-                u_t[free] += step * du_f
-                u_t[fixed] = 0.0
-                backup = st.theta.clone()
-                st.theta += step * dth
-                _, _, rp_t, rd_t = residual_parts(u_t)
-                rt = torch.cat([ap * rp_t, ad * rd_t]) if has_meas else ap * rp_t
-                if float(torch.linalg.vector_norm(rt)) < rt_n * (1.0 - 1e-4 * step):
-                    break  # accepted: theta keeps the trial update (and is advanced again below, nn_solver.py:366-371)
-                st.theta = backup
-                step *= 0.7
-                if step < 1e-10:
-                    step = 0.0
-                    break
-            if 0.0 < step < 1e-8:
-                step = 1e-6
-        if step > 0:
-            u[free] += step * du_f
-            u[fixed] = 0.0
-            st.theta += step * dth
-        rel = rt_n / max(float(torch.linalg.vector_norm(u[free])), config.min_denominator)
-        history.append({"iteration": float(it + 1), "r_physics": rp_n, "r_data": rd_n, "r_total": rt_n,
-                        "relative_error": rel, "step_size": float(step)})
-        print(f"{it + 1:5d} | {rp_n:12.3e} | {rd_n:12.3e} | {rt_n:12.3e} | {step:6.3f}")
-        if rel < config.tolerance and step > 0:
-            converged = True
+            # all trial states at once: u_k = u + s_k du on the free DOFs, theta_k = theta + s_k dtheta
+            u_t = (u[:, None] + du[:, None] * trial_steps[None, :]) * free_mask[:, None]
+            th_t = (st.theta[None, :] + trial_steps[:, None] * dth[None, :]).contiguous()
+            E_t, A_t = trial_fields(th_t)
+            sq_p = 2.0 * plan.residual(u_t.contiguous(), E_t, A_t, f_ext_d, 1.0, f_int=False, r=False, half_sq=True)["half_sq"]
+            if has_meas:
+                rd_t = mv[:, None] - u_t[md]
+                rt_t = torch.sqrt(ap * ap * sq_p + ad * ad * (rd_t * rd_t).sum(0))
+            else:
+                rt_t = torch.sqrt(ap * ap * sq_p)
+            ok = rt_t < rt_n * (1.0 - 1e-4 * trial_steps)
+            any_ok = ok.any()
+            k = torch.argmax(ok.to(torch.int32))  # first accepted trial
+            step = torch.where(any_ok, trial_steps[k], steps[n_trials])
+            # an accepted trial leaves its theta in place and the update below advances it again
+            # (nn_solver.py:309-313 + :366-371); a failed search restores theta and takes the last step once
+            th_mult = torch.where(any_ok, 2.0 * step, step)
+        else:
+            step = torch.ones((), dtype=torch.float64, device=dev)
+            th_mult = step
+        u = (u + step * du) * free_mask
+        st.theta = st.theta + th_mult * dth
+        un = torch.linalg.vector_norm(u[free])
+        rec = torch.stack([rp_n, rd_n, rt_n, step, un, info[0].to(torch.float64)]).cpu()  # the iteration's one sync
+        rp_v, rd_v, rt_v, step_v, un_v, info_v = (float(x) for x in rec)
+        if info_v != 0.0 or not np.isfinite(step_v):
+            # the state was advanced with an undefined step: undo is pointless, the reference stops here too
+            print(f"Solver failed at iteration {it + 1}: Matrix is not positive definite (pivot {int(info_v)})")
             break
-        if step == 0.0:
+        rel = rt_v / max(un_v, config.min_denominator)
+        history.append({"iteration": float(it + 1), "r_physics": rp_v, "r_data": rd_v, "r_total": rt_v,
+                        "relative_error": rel, "step_size": step_v})
+        print(f"{it + 1:5d} | {rp_v:12.3e} | {rd_v:12.3e} | {rt_v:12.3e} | {step_v:6.3f}")
+        if rel < config.tolerance and step_v > 0:
+            converged = True
             break
     unpack_theta(model, st.theta)
     return {"u": u.cpu().numpy(), "converged": converged, "history": history}

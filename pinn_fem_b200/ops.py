@@ -334,6 +334,28 @@ def gn_jacobian(plan: AssemblyPlan, u, E, A, jacE=None, jacA=None, n_rest=0, alp
     return J
 
 
+def gn_lm_step(J: torch.Tensor, R: torch.Tensor, damping_factor: float = 1e-6, path: str = "auto", check_info=True):
+    """One Levenberg-Marquardt step ``dx = -(J^T J + d I)^-1 J^T R`` (fem/nn_solver.py:266-277).  ``path``:
+    ``"auto"`` (dual m x m system when J has fewer rows than columns), ``"primal"`` (n x n), ``"dual"``.
+    Returns ``(dx, damping, info)``; with ``check_info`` a non-positive pivot raises ``RuntimeError`` (one sync),
+    otherwise ``info`` (device int32) is left for the caller to test."""
+    J = _dev_f64(J, "J")
+    R = _dev_f64(R, "R")
+    m, n = J.shape
+    if tuple(R.shape) != (m,):
+        raise ValueError("gn_lm_step: R must have one entry per row of J")
+    dx = torch.empty(n, dtype=torch.float64, device=J.device)
+    damping = torch.empty(1, dtype=torch.float64, device=J.device)
+    info = torch.zeros(1, dtype=torch.int32, device=J.device)
+    with torch.cuda.device(J.device):
+        check(_lib.load().pf_gn_lm_step(m, n, _ptr(J), _ptr(R), float(damping_factor),
+                                        {"auto": 0, "primal": 1, "dual": 2}[path], _ptr(dx), _ptr(damping), _ptr(info),
+                                        _stream_ptr(J.device)))
+    if check_info and int(info[0]) != 0:
+        raise RuntimeError(f"Matrix is not positive definite (pivot {int(info[0])})")
+    return dx, damping, info
+
+
 def gn_normal_equations(J: torch.Tensor, R: torch.Tensor, damping_factor: float = 1e-6):
     """``JtJ + d I`` with ``d = damping_factor * trace(JtJ) / n``, ``Jtr`` and ``d``
     (fem/nn_solver.py:268-274); J^T J runs on the fp64 tensor cores (DMMA)."""

@@ -353,7 +353,7 @@ def test_hybrid_and_scalar_paths(tmp_path, example_inputs, runs):
     assert set(out5["history"][-1]) == set(ref5["history"][-1])  # GD rows + one NR row tagged with "iteration"
 
 
-def test_gauss_newton_solver_vs_oracle(golden_dir, example_inputs, tmp_path):
+def test_gauss_newton_solver_vs_oracle(golden_dir, example_inputs, tmp_path, monkeypatch):
     """C4: compute_jacobian_blocks and a full solve_pinn_newton_raphson run on example 10's model."""
     from pinn_fem_b200.fem import PINNSolverConfig, solve_pinn_newton_raphson
     from pinn_fem_b200.fem.nn_solver import compute_jacobian_blocks
@@ -371,14 +371,44 @@ def test_gauss_newton_solver_vs_oracle(golden_dir, example_inputs, tmp_path):
     mesh = O.Mesh(np.array([[0.0, 0], [1, 0], [2, 0], [3, 0]]), np.array([[0, 1], [1, 2], [2, 3]]),
                   np.array(example_inputs["example10"]["loads"], dtype=float), np.array([0, 1, 3, 5, 7]))
     mat = O.MaterialNets(*[(SPECS[n], g[f"theta0_{n}"].copy(), 1.0) for n in ("young", "area", "density")])
-    u_ref, ok_ref, hist_ref = O.solve_pinn_newton_raphson(mesh, mat, mesh.loads, np.array([1.0, 2, 3]), [2, 4, 6],
-                                                          max_iterations=4)
-    res = solve_pinn_newton_raphson(model, model.loads, np.array([1.0, 2, 3]), [2, 4, 6], PINNSolverConfig(max_iterations=4))
-    assert len(res.history) == len(hist_ref) and res.converged == ok_ref
-    assert abs(res.history[0]["r_total"] - hist_ref[0]["r_total"]) < 1e-12
-    assert abs(res.history[0]["r_total"] - float(g["run_r_total"][0])) < 1e-5  # the reference's own first row
-    assert res.history[0]["step_size"] == hist_ref[0]["step_size"] == float(g["run_step"][0])
-    assert set(res.history[0]) == {"iteration", "r_physics", "r_data", "r_total", "relative_error", "step_size"}
+    # full runs vs the oracle's restatement of the same loop (same quirks), fp64 both sides: every history row, the
+    # final u and theta.  The LM step goes through the m x m dual system here (6 residuals, 1001 unknowns); the
+    # n x n formulation of the reference is run too.  Its matrix is rank 6 plus a 1e-6-relative ridge, so n x n
+    # solves (ours, numpy's) agree with each other and with the dual only to what that conditioning leaves.
+    theta0 = {n: g[f"theta0_{n}"].copy() for n in ("young", "area", "density")}
+    keys = ("iteration", "r_physics", "r_data", "r_total", "relative_error", "step_size")
+    # targets: the example's own (every step accepted at 1), one where iteration 2 is accepted after four rejected
+    # trials (step 0.7^4), one where every trial of iterations 3+ fails (the loop is left with step 0.7^15)
+    cases = (("base", [1.0, 2.0, 3.0], 1.0), ("backtrack", [0.1, 0.2, 0.3], 0.7 ** 4), ("failed", [1.0, -2.0, 3.0], None))
+    # Measured agreement with the oracle over six iterations (scripts/gn_diff_vs_oracle.py): n x n formulation 2e-16 on
+    # the first two rows, <= 1e-8 later; dual formulation 1e-9 on the first row, <= 5e-7 later (the 6 x 6 Gram matrix
+    # has condition ~1e7, so the last-bit differences of J J^T between numpy and the DMMA kernel show at 1e-9 in dx).
+    for path, dual, tol in (("dual", True, 2e-6), ("primal", False, 1e-7)):
+        for case, targets, expect_step in cases:
+            mv = np.array(targets)
+            mat = O.MaterialNets(*[(SPECS[n], theta0[n].copy(), 1.0) for n in ("young", "area", "density")])
+            u_ref, ok_ref, hist_ref = O.solve_pinn_newton_raphson(mesh, mat, mesh.loads, mv, [2, 4, 6], max_iterations=6,
+                                                                  dual=dual)
+            model = _ex_model(example_inputs, None, name="example10", tmp=tmp_path)["model"]
+            monkeypatch.setenv("PF_GN_LM_PATH", path)
+            res = solve_pinn_newton_raphson(model, model.loads, mv, [2, 4, 6], PINNSolverConfig(max_iterations=6))
+            assert len(res.history) == len(hist_ref) == 6 and res.converged == ok_ref
+            for row, ref in zip(res.history, hist_ref):
+                assert set(row) == set(keys)
+                assert row["step_size"] == ref["step_size"] and row["iteration"] == ref["iteration"], (path, case, row, ref)
+                for k in ("r_physics", "r_data", "r_total", "relative_error"):
+                    assert abs(row[k] - ref[k]) <= tol * max(abs(ref[k]), 1e-3), (path, case, row["iteration"], k, row[k], ref[k])
+            assert rel(res.displacements.reshape(-1), u_ref) < tol
+            th = np.concatenate([p.detach().cpu().numpy().reshape(-1) for p in model.material.get_all_torch_params()])
+            assert rel(th, np.concatenate([mat.young[1], mat.area[1], mat.density[1]])) < tol
+            steps_seen = [r["step_size"] for r in hist_ref]
+            if case == "backtrack":
+                assert abs(steps_seen[1] - expect_step) < 1e-15
+            if case == "failed":
+                assert abs(steps_seen[2] - 0.7 ** 15) < 1e-12
+            if case == "base" and path == "dual":
+                assert abs(res.history[0]["r_total"] - float(g["run_r_total"][0])) < 1e-5  # the reference's own first row
+                assert res.history[0]["step_size"] == float(g["run_step"][0])
 
 
 def _api_input(max_iterations):

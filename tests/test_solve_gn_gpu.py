@@ -81,6 +81,28 @@ def test_dense_solve_singular_raises():
         ops.solve_dense(dev(big), dev(np.ones(200)))
 
 
+@pytest.mark.parametrize("n", [3, 150, 700])
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_dense_solve_nan_matrix_raises_instead_of_faulting(n, mode, monkeypatch):
+    """A diverged iterate hands the Newton / LM step a matrix of NaNs.  Every pivot search then finds no candidate
+    (NaN compares false): the small-system kernel, the single-CTA panel and the cluster panel (which used to index
+    distributed shared memory with the INT_MAX sentinel) must report the system as singular, and the device must
+    stay usable."""
+    from pinn_fem_b200 import ops
+
+    monkeypatch.setenv("PF_LU_CLUSTER", mode)
+    rng = np.random.default_rng(n)
+    A = rng.normal(size=(n, n)) + n * np.eye(n)
+    b = rng.normal(size=n)
+    bad = A.copy()
+    bad[:, n // 2:] = np.nan
+    with pytest.raises(RuntimeError, match="Singular"):
+        ops.solve_dense(dev(bad), dev(b))
+    with pytest.raises(RuntimeError, match="Singular"):
+        ops.solve_dense(dev(np.full((n, n), np.nan)), dev(b))
+    assert rel(ops.solve_dense(dev(A), dev(b)), np.linalg.solve(A, b)) < 1e-9  # no sticky error
+
+
 def test_cg_matches_dense_solution():
     from pinn_fem_b200 import AssemblyPlan, ops
 
@@ -188,3 +210,27 @@ def test_cholesky_spd_solve(n):
         bad[n // 2, n // 2] = -1.0
         with pytest.raises(RuntimeError, match="not positive definite"):
             ops.solve_spd(dev(bad), dev(b))
+
+
+@pytest.mark.parametrize("m,n", [(6, 1001), (40, 300), (200, 64), (130, 130)])
+def test_lm_step_dual_and_primal(m, n):
+    """pf_gn_lm_step: dx = -(J^T J + d I)^-1 J^T R through the n x n system and through the m x m dual system
+    (chosen when m < n) against numpy's evaluation of the same two formulas."""
+    from pinn_fem_b200 import ops
+
+    rng = np.random.default_rng(m + n)
+    J = rng.normal(size=(m, n))
+    R = rng.normal(size=m)
+    d = 1e-6 * np.trace(J.T @ J) / n
+    dual_ref = -(J.T @ np.linalg.solve(J @ J.T + d * np.eye(m), R))
+    dx_dual, damp, _ = ops.gn_lm_step(dev(J), dev(R), 1e-6, path="dual")
+    assert abs(float(damp[0]) - d) <= 1e-12 * d
+    assert rel(dx_dual, dual_ref) < (1e-10 if m <= n else 1e-6)  # forced on m > n the dual is the ill-conditioned one
+    dx_auto, _, _ = ops.gn_lm_step(dev(J), dev(R), 1e-6)
+    dx_primal, _, _ = ops.gn_lm_step(dev(J), dev(R), 1e-6, path="primal")
+    assert torch.equal(dx_auto, dx_dual if m < n else dx_primal)
+    # the two formulations are the same vector; the n x n one is solved in a matrix of condition ~1e6 and worse when
+    # m < n (rank-m matrix + ridge), so the agreement is bounded by that, not by the kernels
+    primal_ref = np.linalg.solve(J.T @ J + d * np.eye(n), -(J.T @ R))
+    bound = 1e-9 if m >= n else 1e-5
+    assert rel(dx_primal, primal_ref) < bound and rel(dx_primal, dual_ref) < bound
