@@ -577,9 +577,10 @@ def main():
                                                                    args.gd_iters, dmma_peak)
             launches += extra["pinn_gd_batched_large"].pop("gpu_launches", 0)
             if rank == 0:
-                from bench_gd import example_runs
+                from bench_gd import example_runs, gn_iteration_leg
 
                 extra["examples"] = example_runs(ROOT / "tests" / "golden" / "inputs")
+                extra["gauss_newton_example10"] = gn_iteration_leg(ROOT / "tests" / "golden" / "inputs")
             if world > 1:
                 from bench_gd import gd_element_sharded_iterations_per_second
 

@@ -280,6 +280,66 @@ def gd_element_sharded_iterations_per_second(device, nodes, elements, fixed, wor
     return res
 
 
+def gn_iteration_leg(golden_inputs_dir, iters=10):
+    """seconds per Gauss-Newton / LM iteration on example 10's model (4-node bar, three
+    networks, J 6 x 1001, targets u = [1, 2, 3] at DOFs [2, 4, 6], line search on) through
+    fem.nn_solver.solve_pinn_newton_raphson, next to the CPU restatement of the reference's
+    compute_jacobian_blocks + nn_solver.py:266-277 (the reference itself is not on the GPU box; BASELINE.md
+    records 0.12 s per compute_jacobian_blocks call for it on the survey container)."""
+    import io
+    import json
+    import tempfile
+    import time
+    from contextlib import redirect_stdout
+    from pathlib import Path
+
+    from oracle import pinnfem_oracle as O
+    from pinn_fem_b200.examples.json import generic
+    from pinn_fem_b200.fem import PINNSolverConfig, solve_pinn_newton_raphson
+
+    src = Path(golden_inputs_dir) / "example10.json"
+    mv, md = np.array([1.0, 2.0, 3.0]), [2, 4, 6]
+    out = {"workload": "example 10's model: 3 elements, 3 networks (998 parameters, 837 reach the loss), J 6 x 1001, "
+                       "line search with 15 trial steps evaluated as one batch, LM step through the 6 x 6 dual system"}
+    with tempfile.TemporaryDirectory() as tmp:
+        dst = Path(tmp) / src.name
+        dst.write_text(src.read_text())
+        best = None
+        for rep in range(3):
+            torch.manual_seed(0)
+            with redirect_stdout(io.StringIO()):
+                model = generic.parse_problem(str(dst))["model"]
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                res = solve_pinn_newton_raphson(model, model.loads, mv, md, PINNSolverConfig(max_iterations=iters, tolerance=0.0))
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out["gpu_s_per_iteration"] = best / len(res.history)
+        out["iterations"] = len(res.history)
+        out["host_syncs_per_iteration"] = 1
+    # CPU: the oracle's restatement of compute_jacobian_blocks (closed form, no autograd) + the n x n LM solve
+    SPECS = [O.NetSpec(3, 2, 20), O.NetSpec(3, 2, 15), O.NetSpec(3, 2, 10)]
+    torch.manual_seed(0)
+    nets = [generic.SimpleNN(2, w, 3) for w in (20, 15, 10)]
+    th = [torch.cat([q.detach().reshape(-1).double() for q in n.parameters()]).numpy() for n in nets]
+    mesh = O.Mesh(NODES, ELEMENTS, LOADS, FIXED)
+    mat = O.MaterialNets(*[(sp, t.copy(), 1.0) for sp, t in zip(SPECS, th)])
+    u = np.array([0, 0, 0.5, 0, 1.0, 0, 1.5, 0])
+    cpu = None
+    for rep in range(5):
+        t0 = time.perf_counter()
+        j_uu, j_ut, r_p, j_du = O.jacobian_blocks(mesh, mat, u, mesh.loads, np.array(md), 1.0)
+        J, R = O.gauss_newton_system(j_uu, j_ut, r_p, j_du, mv - u[md], 1.0, 1.0)
+        O.lm_step(J, R)
+        dt = time.perf_counter() - t0
+        cpu = dt if cpu is None else min(cpu, dt)
+    out["cpu_port_s_per_jacobian_and_lm_solve"] = cpu
+    out["cpu_note"] = ("numpy restatement (closed-form Jacobian, 1001 x 1001 LU), one core, no line search; the reference's own "
+                       "compute_jacobian_blocks (998 + 3 autograd passes) took 0.12 s per call on the survey container (BASELINE.md)")
+    return out
+
+
 def example_runs(golden_inputs_dir, names=("example1", "example4-P", "example7-P")):
     """BASELINE.json configs[0..2]: whole ``generic.py`` solves (parse + solve + post-processing, seed 0) of the
     reference's own example files, timed warm (second run) on the wall clock, next to the reference's timings
